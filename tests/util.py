@@ -45,6 +45,6 @@ def normwise(new, ref, floor=0.0):
     return num / den
 
 
-def grad_floor(rec, frac=1e-3, prefix='g.'):
+def grad_floor(rec, frac=1e-2, prefix='g.'):
     """frac x the largest reference gradient entry over all parameters of a golden record."""
     return frac * max(v.abs().max().item() for k, v in rec.items() if k.startswith(prefix))
