@@ -1,0 +1,107 @@
+/* libmmnas_b200 — C ABI of the B200-native MMnas operator hot path.
+ *
+ * The reference (MILVLG/mmnas) has no FFI of its own: its operator path is pure PyTorch
+ * (mmnas/model/modules.py, mmnas/model/mixed.py).  These entry points are what a binding for that path
+ * binds instead of torch's nn.Linear / torch.matmul / F.softmax / masked_fill / nn.Dropout / x.std calls;
+ * each one cites the reference lines it replaces.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise;
+ *   - `stream` is a cudaStream_t; every call is asynchronous on it, allocates nothing, keeps no state
+ *     between calls and is safe to capture in a CUDA graph;
+ *   - return 0 on success, <0 on error (MMNAS_ERR_*); mmnas_last_error() gives a thread-local message;
+ *   - dtype arguments: 0 = float32, 1 = bfloat16 (storage type; all arithmetic accumulates in fp32);
+ *   - dropout: `rng_state` is a device array {seed, step} of two uint64 (NULL or p == 0 disables it);
+ *     `salt` identifies the call site; element i of a site is kept iff hash16(seed, step, salt, i) >= p*65536
+ *     and scaled by 1/(1-p).  Forward and backward of one site pass identical (rng_state, salt, p).
+ *   - tensors are row-major; "ld" is a row pitch in ELEMENTS.
+ */
+#ifndef MMNAS_B200_H
+#define MMNAS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMNAS_B200_ABI_VERSION 1
+
+typedef void* mmnas_stream;
+
+int mmnas_abi_version(void);
+const char* mmnas_last_error(void);
+
+/* ---- dense contractions: nn.Linear forward/backward (modules.py:18,38,172-175,216-220) ----------------
+ * fp32 arm (FFMA): C[M,N] = epi(A @ B (+bias[N])) (+C);  A(m,k) = A[m*a_rs + k*a_cs], B(k,n) = B[k*b_rs + n*b_cs].
+ * epilogue: 0 none, 1 ReLU (FC.relu :27), 2 ReLU+dropout (:29), 3 C = aux[m,n] > 0 ? v*aux_scale : 0 (ReLU/dropout backward). */
+int mmnas_gemm_f32(int M, int N, int K, const float* A, long a_rs, long a_cs, const float* B, long b_rs, long b_cs,
+                   float* C, long ldc, const float* bias, int epilogue, int accumulate, const float* aux, long ld_aux,
+                   float aux_scale, const unsigned long long* rng_state, unsigned long long salt, float p,
+                   mmnas_stream stream);
+
+/* bf16 arm (tcgen05/TMEM/TMA).  A: a_mn_major 0 -> stored [M][K] (pitch lda), 1 -> stored [K][M];
+ * B: b_mn_major 0 -> stored [N][K] (pitch ldb), 1 -> stored [K][N].  C fp32 or bf16 [M][N] (pitch ldc).
+ * relu / dropout / aux-mask (aux is bf16 [M][N]) / accumulate (fp32 C += result) as above; split_k > 1 adds
+ * the partial products into a caller-zeroed fp32 C with red.add (weight gradients, reduction over tokens).
+ * Requirements: N % 32 == 0, pitches % 8 == 0, 16-byte aligned bases. */
+int mmnas_gemm_bf16(int M, int N, int K, const void* A, long lda, int a_mn_major, const void* B, long ldb,
+                    int b_mn_major, void* C, long ldc, int out_bf16, const float* bias, int relu, int accumulate,
+                    const void* aux, long ld_aux, float aux_scale, int split_k, const unsigned long long* rng_state,
+                    unsigned long long salt, float p, mmnas_stream stream);
+
+/* ---- attention core: MHAtt.att (modules.py:190-199) / RelMHAtt.forward (:232-240) ---------------------
+ * q [B*Nq rows, pitch ldq], k/v [B*Nk rows]; head h reads columns [h*64, h*64+64).  kmask [B,Nk] bytes, 1 = padded
+ * key (masked_fill(mask, -1e9) AFTER the bias add); bias [B,heads,Nq,Nk] fp32 or NULL; o [B*Nq rows, pitch ldo]
+ * in merged-head layout.  Nk <= 128, head_dim == 64. */
+int mmnas_attn_fwd(int dtype, int B, int heads, int Nq, int Nk, int head_dim, const void* q, long ldq, const void* k,
+                   long ldk, const void* v, long ldv, const unsigned char* kmask, const float* bias, void* o, long ldo,
+                   float scale, const unsigned long long* rng_state, unsigned long long salt, float p,
+                   mmnas_stream stream);
+/* Backward: recomputes the attention map; dbias (fp32 [B,heads,Nq,Nk], = dS) is written when non-NULL. */
+int mmnas_attn_bwd(int dtype, int B, int heads, int Nq, int Nk, int head_dim, const void* q, long ldq, const void* k,
+                   long ldk, const void* v, long ldv, const unsigned char* kmask, const float* bias, const void* o,
+                   long ldo, const void* dout, long lddo, void* dq, long lddq, void* dk, long lddk, void* dv, long lddv,
+                   float* dbias, float scale, const unsigned long long* rng_state, unsigned long long salt, float p,
+                   mmnas_stream stream);
+
+/* ---- RSA geometry bias: log(clamp(relu(linear_r(rel_embed)), 1e-6)) (modules.py:231,235) --------------
+ * Exactly one of rel [B,N,N,R] (the reference's dense tensor) or g4 [B,N,N,4] (+Wy [R,4], by [R]: the
+ * relu(linear_y_rel(.)) of full_vqa.py:103 folded in) is non-NULL.  bias out: [B,heads,N,N].  R == 64, heads <= 16. */
+int mmnas_relbias_fwd(int B, int N, int heads, int R, const float* rel, const float* g4, const float* Wy,
+                      const float* by, const float* Wr, const float* br, float* bias, mmnas_stream stream);
+/* Backward: dWr/dbr (and dWy/dby, geometry mode) are ACCUMULATED (caller zeroes); drel [B,N,N,R] written (dense mode). */
+int mmnas_relbias_bwd(int B, int N, int heads, int R, const float* rel, const float* g4, const float* Wy,
+                      const float* by, const float* Wr, const float* br, const float* dbias, float* drel, float* dWy,
+                      float* dby, float* dWr, float* dbr, mmnas_stream stream);
+
+/* ---- block tail: x + dropout(branch) -> LayerNorm (modules.py:261-271 and :52-56) ----------------------
+ * On return `branch` holds z = x + dropout(branch) (saved for backward).  gamma/beta NULL = norm off; x NULL =
+ * residual off.  out_bf16 (optional) receives a bf16 copy of `out` for the next block's tensor-core GEMM. */
+int mmnas_ln_residual_fwd(int rows, int H, const float* x, float* branch, const float* gamma, const float* beta,
+                          float eps, float* out, void* out_bf16, float* mean, float* sigma,
+                          const unsigned long long* rng_state, unsigned long long salt, float p, mmnas_stream stream);
+/* dz = grad wrt z (also the residual-path grad wrt x); dbranch = dz * dropout mask (dtype 0/1; may be NULL);
+ * dgamma/dbeta are ACCUMULATED (caller zeroes).  H <= 1024. */
+int mmnas_ln_residual_bwd(int rows, int H, const float* dout, const float* z, const float* mean, const float* sigma,
+                          const float* gamma, float eps, float* dz, void* dbranch, int dbranch_dtype, float* dgamma,
+                          float* dbeta, const unsigned long long* rng_state, unsigned long long salt, float p,
+                          mmnas_stream stream);
+
+/* ---- supernet mixed-op: MixedOp.forward 'full' mode (mixed.py:60-68) -----------------------------------
+ * out = sum_k gate[k] * outs[k]   (outs: HOST array of K device pointers, each n floats; n % 4 == 0; K <= 8) */
+int mmnas_mixed_accum(int K, const float* const* outs, const float* gate, float* out, long n, mmnas_stream stream);
+/* gate_grad[k] = <outs[k], dout> (overwritten) — autograd's alpha_gate.grad; d_outs[k] (HOST array, entries may be
+ * NULL for detached candidates) receives gate[k] * dout. */
+int mmnas_mixed_alpha_dot(int K, const float* const* outs, const float* gate, const float* dout, float* gate_grad,
+                          float* const* d_outs, long n, mmnas_stream stream);
+
+/* ---- helpers -------------------------------------------------------------------------------------------- */
+int mmnas_cast_f32_to_bf16(const float* src, void* dst, long n, mmnas_stream stream);
+/* out[c] = sum_r x[r,c] (bias gradients); out is overwritten. */
+int mmnas_colsum(int dtype, const void* x, int rows, int cols, long ld, float* out, mmnas_stream stream);
+/* state[1] += 1: call once per training step so every step draws fresh dropout masks (graph-capturable). */
+int mmnas_rng_advance(unsigned long long* state, mmnas_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

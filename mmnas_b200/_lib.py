@@ -1,0 +1,99 @@
+"""ctypes binding of libmmnas_b200.so (the C ABI declared in include/mmnas_b200.h).
+
+There is deliberately NO fallback: if the library is missing or a call fails, this raises.  PyTorch is
+used for device memory and streams only; every argument crossing this boundary is a raw device
+pointer, a size or a scalar."""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libmmnas_b200.so')
+ABI_VERSION = 1
+
+c_p, c_i, c_l, c_f, c_u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float, ctypes.c_ulonglong
+
+# name -> argtypes, in header order
+SIGNATURES = {
+    'mmnas_gemm_f32': [c_i, c_i, c_i, c_p, c_l, c_l, c_p, c_l, c_l, c_p, c_l, c_p, c_i, c_i, c_p, c_l, c_f, c_p, c_u64,
+                       c_f, c_p],
+    'mmnas_gemm_bf16': [c_i, c_i, c_i, c_p, c_l, c_i, c_p, c_l, c_i, c_p, c_l, c_i, c_p, c_i, c_i, c_p, c_l, c_f, c_i,
+                        c_p, c_u64, c_f, c_p],
+    'mmnas_attn_fwd': [c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_l, c_p, c_l, c_p, c_l, c_p, c_p, c_p, c_l, c_f, c_p, c_u64,
+                       c_f, c_p],
+    'mmnas_attn_bwd': [c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_l, c_p, c_l, c_p, c_l, c_p, c_p, c_p, c_l, c_p, c_l, c_p,
+                       c_l, c_p, c_l, c_p, c_l, c_p, c_f, c_p, c_u64, c_f, c_p],
+    'mmnas_relbias_fwd': [c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
+    'mmnas_relbias_bwd': [c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
+    'mmnas_ln_residual_fwd': [c_i, c_i, c_p, c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_p, c_p, c_u64, c_f, c_p],
+    'mmnas_ln_residual_bwd': [c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_f, c_p, c_p, c_i, c_p, c_p, c_p, c_u64, c_f, c_p],
+    'mmnas_mixed_accum': [c_i, c_p, c_p, c_p, c_l, c_p],
+    'mmnas_mixed_alpha_dot': [c_i, c_p, c_p, c_p, c_p, c_p, c_l, c_p],
+    'mmnas_cast_f32_to_bf16': [c_p, c_p, c_l, c_p],
+    'mmnas_colsum': [c_i, c_p, c_i, c_i, c_l, c_p, c_p],
+    'mmnas_rng_advance': [c_p, c_p],
+}
+
+_lib = None
+
+
+class MMnasLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built — never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MMnasLibraryError(
+            'libmmnas_b200.so is not built (%s). Run `python -m mmnas_b200.build`; there is no CPU or '
+            'PyTorch fallback for the operator hot path.' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.mmnas_abi_version.restype = c_i
+    lib.mmnas_last_error.restype = ctypes.c_char_p
+    if lib.mmnas_abi_version() != ABI_VERSION:
+        raise MMnasLibraryError('libmmnas_b200.so ABI %d != binding ABI %d; rebuild' % (lib.mmnas_abi_version(), ABI_VERSION))
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = c_i
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise MMnasLibraryError('%s failed (%d): %s' % (name, rc, lib.mmnas_last_error().decode()))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return t
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise MMnasLibraryError('mmnas_b200 operators run on CUDA tensors only (got a %s tensor); '
+                                    'there is no CPU path.' % t.device)
+
+
+def ptr_array(tensors):
+    """Host array of device pointers (NULL for None entries)."""
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr

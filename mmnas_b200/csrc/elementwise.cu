@@ -1,0 +1,192 @@
+// HBM-bound helpers of the hot path: fp32->bf16 casts (operand shadows for the tensor-core GEMMs),
+// column sums (bias gradients), the supernet mixed-op accumulate and its alpha-gate gradient
+// (mixed.py:60-68 and the autograd rule SURVEY §8 a11), and the dropout step counter.
+// All are vectorised (float4 / 8-byte bf16x4), grid-stride, grid = k x 148 SMs.
+#include "common.cuh"
+#include "../../include/mmnas_b200.h"
+
+namespace {
+
+constexpr int EW_THREADS = 256;
+inline int ew_grid(long nvec) {
+  long want = (nvec + EW_THREADS - 1) / EW_THREADS;
+  long cap = 148 * 8;
+  return (int)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+__global__ void __launch_bounds__(EW_THREADS) cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long n) {
+  const long nvec = n >> 2;
+  for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (long)gridDim.x * blockDim.x) {
+    float4 f = *reinterpret_cast<const float4*>(src + 4 * v);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(f.x, f.y), hi = __floats2bfloat162_rn(f.z, f.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<unsigned*>(&lo);
+    pk.y = *reinterpret_cast<unsigned*>(&hi);
+    *reinterpret_cast<uint2*>(dst + 4 * v) = pk;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    long i = (nvec << 2) + threadIdx.x;
+    dst[i] = __float2bfloat16_rn(src[i]);
+  }
+}
+
+// out[c] = sum_r x[r, c];  CTA (32 x 8) owns 32 columns and a slab of rows; smem combine; atomics.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, int rows, int cols, long ld, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (c < cols)
+    for (int r = blockIdx.y * 8 + ty; r < rows; r += gridDim.y * 8) s += to_f32<T>(x[(long)r * ld + c]);
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot += red[k][tx];
+    atomicAdd(&out[c], tot);
+  }
+}
+
+constexpr int MAXK = 8;
+struct MixedArgs {
+  int K;
+  const float* o[MAXK];
+  float* d_o[MAXK];
+  const float* gate;
+  const float* dout;
+  float* out;
+  float* gate_grad;
+  long n;
+};
+
+__global__ void __launch_bounds__(EW_THREADS) mixed_accum_kernel(MixedArgs a) {
+  float g[MAXK];
+#pragma unroll
+  for (int k = 0; k < MAXK; ++k) g[k] = k < a.K ? a.gate[k] : 0.f;
+  const long nvec = a.n >> 2;
+  for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (long)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < MAXK; ++k)
+      if (k < a.K) {
+        float4 o = *reinterpret_cast<const float4*>(a.o[k] + 4 * v);
+        acc.x = fmaf(g[k], o.x, acc.x); acc.y = fmaf(g[k], o.y, acc.y);
+        acc.z = fmaf(g[k], o.z, acc.z); acc.w = fmaf(g[k], o.w, acc.w);
+      }
+    *reinterpret_cast<float4*>(a.out + 4 * v) = acc;
+  }
+}
+
+// gate_grad[k] = <o_k, dout>;  d_o[k] = gate[k] * dout for the candidates that take gradient.
+__global__ void __launch_bounds__(EW_THREADS) mixed_alpha_dot_kernel(MixedArgs a) {
+  __shared__ float red[MAXK][EW_THREADS / 32];
+  float g[MAXK], dot[MAXK];
+#pragma unroll
+  for (int k = 0; k < MAXK; ++k) { g[k] = k < a.K ? a.gate[k] : 0.f; dot[k] = 0.f; }
+  const long nvec = a.n >> 2;
+  for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (long)gridDim.x * blockDim.x) {
+    const float4 d = *reinterpret_cast<const float4*>(a.dout + 4 * v);
+#pragma unroll
+    for (int k = 0; k < MAXK; ++k)
+      if (k < a.K) {
+        const float4 o = *reinterpret_cast<const float4*>(a.o[k] + 4 * v);
+        dot[k] += (o.x * d.x + o.y * d.y) + (o.z * d.z + o.w * d.w);
+        if (a.d_o[k]) {
+          float4 r = make_float4(g[k] * d.x, g[k] * d.y, g[k] * d.z, g[k] * d.w);
+          *reinterpret_cast<float4*>(a.d_o[k] + 4 * v) = r;
+        }
+      }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < MAXK; ++k) {
+    float s = warp_sum(dot[k]);
+    if (lane == 0) red[k][warp] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < a.K) {
+    float tot = 0.f;
+    for (int w = 0; w < EW_THREADS / 32; ++w) tot += red[threadIdx.x][w];
+    atomicAdd(&a.gate_grad[threadIdx.x], tot);
+  }
+}
+
+__global__ void rng_advance_kernel(unsigned long long* state) { state[1] += 1ull; }
+
+}  // namespace
+
+extern "C" int mmnas_cast_f32_to_bf16(const float* src, void* dst, long n, mmnas_stream stream) {
+  MMNAS_CHECK_ARG(n >= 0, "cast: negative length");
+  if (n == 0) return MMNAS_OK;
+  MMNAS_CHECK_ARG(src && dst, "cast: null buffer");
+  MMNAS_CHECK_ARG(((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 8) == 0, "cast: buffers must be 16-byte aligned");
+  cast_kernel<<<ew_grid(n >> 2), EW_THREADS, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+  MMNAS_LAUNCH_CHECK();
+  return MMNAS_OK;
+}
+
+extern "C" int mmnas_colsum(int dtype, const void* x, int rows, int cols, long ld, float* out, mmnas_stream stream) {
+  MMNAS_CHECK_ARG(dtype == 0 || dtype == 1, "colsum: dtype");
+  MMNAS_CHECK_ARG(rows >= 0 && cols > 0 && x && out, "colsum: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  MMNAS_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, s));
+  if (rows == 0) return MMNAS_OK;
+  int gy = ceil_div(rows, 8 * 16);
+  if (gy > 64) gy = 64;
+  dim3 grid(ceil_div(cols, 32), gy);
+  if (dtype == 0) colsum_kernel<float><<<grid, 256, 0, s>>>((const float*)x, rows, cols, ld, out);
+  else colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, rows, cols, ld, out);
+  MMNAS_LAUNCH_CHECK();
+  return MMNAS_OK;
+}
+
+extern "C" int mmnas_mixed_accum(int K, const float* const* outs, const float* gate, float* out, long n,
+                                 mmnas_stream stream) {
+  MMNAS_CHECK_ARG(K >= 1 && K <= MAXK, "mixed_accum: 1..8 candidates");
+  MMNAS_CHECK_ARG(outs && gate && out && n >= 0 && (n % 4) == 0, "mixed_accum: bad argument (n must be a multiple of 4)");
+  if (n == 0) return MMNAS_OK;
+  MixedArgs a = {};
+  a.K = K; a.gate = gate; a.out = out; a.n = n;
+  for (int k = 0; k < K; ++k) { MMNAS_CHECK_ARG(outs[k], "mixed_accum: null candidate output"); a.o[k] = outs[k]; }
+  mixed_accum_kernel<<<ew_grid(n >> 2), EW_THREADS, 0, (cudaStream_t)stream>>>(a);
+  MMNAS_LAUNCH_CHECK();
+  return MMNAS_OK;
+}
+
+extern "C" int mmnas_mixed_alpha_dot(int K, const float* const* outs, const float* gate, const float* dout,
+                                     float* gate_grad, float* const* d_outs, long n, mmnas_stream stream) {
+  MMNAS_CHECK_ARG(K >= 1 && K <= MAXK, "mixed_alpha_dot: 1..8 candidates");
+  MMNAS_CHECK_ARG(outs && gate && dout && gate_grad && n >= 0 && (n % 4) == 0, "mixed_alpha_dot: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  MMNAS_CUDA(cudaMemsetAsync(gate_grad, 0, sizeof(float) * K, s));
+  if (n == 0) return MMNAS_OK;
+  MixedArgs a = {};
+  a.K = K; a.gate = gate; a.dout = dout; a.gate_grad = gate_grad; a.n = n;
+  for (int k = 0; k < K; ++k) {
+    MMNAS_CHECK_ARG(outs[k], "mixed_alpha_dot: null candidate output");
+    a.o[k] = outs[k];
+    a.d_o[k] = d_outs ? d_outs[k] : nullptr;
+  }
+  mixed_alpha_dot_kernel<<<ew_grid(n >> 2), EW_THREADS, 0, s>>>(a);
+  MMNAS_LAUNCH_CHECK();
+  return MMNAS_OK;
+}
+
+extern "C" int mmnas_rng_advance(unsigned long long* state, mmnas_stream stream) {
+  MMNAS_CHECK_ARG(state, "rng_advance: null state");
+  rng_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state);
+  MMNAS_LAUNCH_CHECK();
+  return MMNAS_OK;
+}
+
+// ---- error string / ABI version ------------------------------------------------------------
+static thread_local char g_err[256] = "";
+void mmnas_set_error(const char* msg) {
+  int i = 0;
+  for (; msg && msg[i] && i < 255; ++i) g_err[i] = msg[i];
+  g_err[i] = 0;
+}
+extern "C" const char* mmnas_last_error(void) { return g_err; }
+extern "C" int mmnas_abi_version(void) { return MMNAS_B200_ABI_VERSION; }

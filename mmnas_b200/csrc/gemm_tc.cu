@@ -1,0 +1,355 @@
+// bf16 tensor-core GEMM for sm_100a: TMA (cp.async.bulk.tensor) -> 128B-swizzled shared memory ->
+// tcgen05.mma (cta_group::1, 128xBNx16, kind::f16, fp32 accumulate in TMEM) -> tcgen05.ld epilogue.
+// Serves every dense contraction of the MMnas blocks in bf16 mode:
+//   forward   Y = X W^T        A K-major  [M,K],  B K-major  [N,K]            (nn.Linear, modules.py:18,38,172-175)
+//   dgrad     dX = dY W        A K-major  [M,N'], B MN-major (W itself, [N',K'])
+//   wgrad     dW = dY^T X      A MN-major (dY, [M,N']), B MN-major (X, [M,K'])  + split-K over M
+// so no transposed copies of activations or weights are ever materialised.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer (one elected
+// lane), warps 2..5 = epilogue (each owns the 32 TMEM lanes of its warp%4 quarter).
+// Fused epilogues: +bias, ReLU, dropout, ReLU-mask of a saved activation (FFN backward),
+// accumulate into fp32 C (residual-gradient add), bf16 or fp32 store, split-K red.add.
+#include <cuda.h>
+#include "common.cuh"
+#include "../../include/mmnas_b200.h"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
+constexpr int A_TILE_BYTES = BM * BK * 2, B_TILE_BYTES = BN * BK * 2;
+constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int NUM_THREADS = 192;
+constexpr uint32_t TMEM_COLS = BN;
+
+struct TcEpilogue {
+  int M, N, K;
+  void* C; long ldc; int out_bf16;
+  const float* bias;
+  int relu;
+  int accumulate;                    // fp32 out: C += result (plain RMW; split_k == 1)
+  const __nv_bfloat16* aux; long ld_aux; float aux_scale;   // C = aux > 0 ? v * aux_scale : 0
+  int use_drop; DropCfg drop;
+  int split_k;                       // > 1: fp32 red.add into C
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// shared-memory matrix descriptor, SWIZZLE_128B, sm_100 version bit (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// instruction descriptor for kind::f16: bf16 x bf16 -> f32 (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS)
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, TcEpilogue ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  // bars[0..S) full, bars[S..2S) empty, bars[2S] tmem_full; then the TMEM base address word
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+  // split-K: this CTA reduces k-blocks [kb_begin, kb_end)
+  const int kb_total = (ep.K + BK - 1) / BK;
+  const int kb_per = (kb_total + ep.split_k - 1) / ep.split_k;
+  const int kb_begin = blockIdx.z * kb_per;
+  const int kb_end = min(kb_total, kb_begin + kb_per);
+  const int num_kb = kb_end - kb_begin;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (num_kb > 0) {
+    if (warp == 0 && lane == 0) {
+      // ===== TMA producer =====
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t phase = (i / STAGES) & 1;
+        mbar_wait(empty_bar(s), phase ^ 1);
+        mbar_expect_tx(full_bar(s), STAGE_BYTES);
+        const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_TILE_BYTES;
+        const int k0 = (kb_begin + i) * BK;
+        if (!A_MN) {
+          tma_load_2d(sa, &tmap_a, full_bar(s), k0, m0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * (BK * 128), &tmap_a, full_bar(s), m0 + 64 * c, k0);
+        }
+        if (!B_MN) {
+          tma_load_2d(sb, &tmap_b, full_bar(s), k0, n0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * (BK * 128), &tmap_b, full_bar(s), n0 + 64 * c, k0);
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc(A_MN, B_MN, BM, BN);
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t phase = (i / STAGES) & 1;
+        mbar_wait(full_bar(s), phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_TILE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) {
+          // K-major: 16 k-elements = 32 B inside the 128 B swizzle row; SBO = 8 rows x 128 B.
+          // MN-major: 16 k-rows x 128 B = 2048 B; SBO = 8 k-rows x 128 B, LBO = next 64-wide MN chunk.
+          const uint64_t adesc = A_MN ? make_smem_desc(sa + kk * 2048, BK * 128, 1024) : make_smem_desc(sa + kk * 32, 16, 1024);
+          const uint64_t bdesc = B_MN ? make_smem_desc(sb + kk * 2048, BK * 128, 1024) : make_smem_desc(sb + kk * 32, 16, 1024);
+          umma_bf16(tmem_base, adesc, bdesc, idesc, (i | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));        // frees the smem stage when these MMAs retire
+      }
+      umma_commit(tmem_full_bar);         // accumulator complete
+    }
+  }
+
+  if (warp >= 2) {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32)
+    const int row = m0 + quarter * 32 + lane;
+    if (num_kb > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    const uint64_t key = ep.use_drop ? drop_key(ep.drop) : 0;
+    const bool add_bias = ep.bias != nullptr && blockIdx.z == 0;
+#pragma unroll 1
+    for (int cc = 0; cc < BN / 32; ++cc) {
+      const int col0 = n0 + cc * 32;
+      if (col0 >= ep.N) break;                    // warp-uniform (N % 32 == 0)
+      uint32_t r[32];
+      if (num_kb > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cc * 32), r);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = 0u;
+      }
+      if (row < ep.M) {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float x = __uint_as_float(r[i]);
+          if (add_bias) x += __ldg(ep.bias + col0 + i);
+          if (ep.relu) x = fmaxf(x, 0.f);
+          if (ep.use_drop) x *= drop_mult(key, (uint64_t)row * ep.N + col0 + i, ep.drop.thresh, ep.drop.scale);
+          v[i] = x;
+        }
+        if (ep.aux) {
+          const uint4* ap = reinterpret_cast<const uint4*>(ep.aux + (long)row * ep.ld_aux + col0);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 pk = __ldg(ap + g);
+            const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&pk);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[g * 8 + i] = __bfloat162float(hb[i]) > 0.f ? v[g * 8 + i] * ep.aux_scale : 0.f;
+          }
+        }
+        if (ep.out_bf16) {
+          __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(ep.C) + (long)row * ep.ldc + col0;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 pk;
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[g * 8 + 0], v[g * 8 + 1]);
+            __nv_bfloat162 t1 = __floats2bfloat162_rn(v[g * 8 + 2], v[g * 8 + 3]);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[g * 8 + 4], v[g * 8 + 5]);
+            __nv_bfloat162 t3 = __floats2bfloat162_rn(v[g * 8 + 6], v[g * 8 + 7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+            pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+            *reinterpret_cast<uint4*>(cp + g * 8) = pk;
+          }
+        } else {
+          float* cp = reinterpret_cast<float*>(ep.C) + (long)row * ep.ldc + col0;
+          if (ep.split_k > 1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) atomicAdd(cp + i, v[i]);
+          } else {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              float4 o = make_float4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+              if (ep.accumulate) {
+                const float4 old = *reinterpret_cast<const float4*>(cp + g * 4);
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+              }
+              *reinterpret_cast<float4*>(cp + g * 4) = o;
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host side: tensor maps through the driver entry point (no libcuda link dependency) -------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor, `inner` contiguous elements per row, `outer` rows of pitch ld elements.
+int encode_2d(CUtensorMap* m, const void* base, long inner, long outer, long ld, int box_inner, int box_outer) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { mmnas_set_error("cuTensorMapEncodeTiled entry point not available"); return MMNAS_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { mmnas_set_error("cuTensorMapEncodeTiled failed (alignment / stride?)"); return MMNAS_ERR_CUDA; }
+  return MMNAS_OK;
+}
+
+}  // namespace
+
+extern "C" int mmnas_gemm_bf16(int M, int N, int K, const void* A, long lda, int a_mn_major, const void* B, long ldb,
+                               int b_mn_major, void* C, long ldc, int out_bf16, const float* bias, int relu,
+                               int accumulate, const void* aux, long ld_aux, float aux_scale, int split_k,
+                               const unsigned long long* rng_state, unsigned long long salt, float p,
+                               mmnas_stream stream) {
+  MMNAS_CHECK_ARG(M >= 0 && N >= 0 && K >= 0, "gemm_bf16: negative size");
+  if (M == 0 || N == 0) return MMNAS_OK;
+  MMNAS_CHECK_ARG(A && B && C, "gemm_bf16: null operand");
+  MMNAS_CHECK_ARG(N % 32 == 0, "gemm_bf16: N must be a multiple of 32");
+  MMNAS_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "gemm_bf16: operand pitches must be multiples of 8 elements (16 B)");
+  MMNAS_CHECK_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)C % 16) == 0, "gemm_bf16: 16-byte alignment");
+  MMNAS_CHECK_ARG(ldc % (out_bf16 ? 8 : 4) == 0, "gemm_bf16: ldc alignment");
+  if (split_k < 1) split_k = 1;
+  const int kb_total = ceil_div(K > 0 ? K : 1, BK);
+  if (split_k > kb_total) split_k = kb_total;
+  MMNAS_CHECK_ARG(split_k == 1 || (!out_bf16 && !relu && !aux && !accumulate && !(p > 0.f)),
+                  "gemm_bf16: split-K only supports the plain / bias fp32 epilogue");
+  MMNAS_CHECK_ARG(!accumulate || !out_bf16, "gemm_bf16: accumulate needs fp32 output");
+  MMNAS_CHECK_ARG(!aux || ld_aux % 8 == 0, "gemm_bf16: aux pitch");
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a_mn_major) rc = encode_2d(&ta, A, K, M, lda, BK, BM);     // [M rows][K contiguous]
+  else rc = encode_2d(&ta, A, M, K, lda, 64, BK);                 // [K rows][M contiguous]
+  if (rc) return rc;
+  if (!b_mn_major) rc = encode_2d(&tb, B, K, N, ldb, BK, BN);     // [N rows][K contiguous]
+  else rc = encode_2d(&tb, B, N, K, ldb, 64, BK);                 // [K rows][N contiguous]
+  if (rc) return rc;
+  TcEpilogue ep = {};
+  ep.M = M; ep.N = N; ep.K = K; ep.C = C; ep.ldc = ldc; ep.out_bf16 = out_bf16; ep.bias = bias; ep.relu = relu;
+  ep.accumulate = accumulate; ep.aux = (const __nv_bfloat16*)aux; ep.ld_aux = ld_aux; ep.aux_scale = aux_scale;
+  ep.split_k = split_k;
+  ep.use_drop = (p > 0.f && rng_state) ? 1 : 0;
+  ep.drop.state = rng_state; ep.drop.salt = salt;
+  ep.drop.thresh = (unsigned)(p * 65536.f + 0.5f); ep.drop.scale = p < 1.f ? 1.f / (1.f - p) : 0.f;
+  dim3 grid(ceil_div(N, BN), ceil_div(M, BM), split_k);
+  cudaStream_t s = (cudaStream_t)stream;
+  static bool attr_done = false;
+  if (!attr_done) {
+    MMNAS_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    MMNAS_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    MMNAS_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    MMNAS_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_done = true;
+  }
+  if (!a_mn_major && !b_mn_major) gemm_bf16_tc_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta, tb, ep);
+  else if (!a_mn_major && b_mn_major) gemm_bf16_tc_kernel<false, true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta, tb, ep);
+  else if (a_mn_major && !b_mn_major) gemm_bf16_tc_kernel<true, false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta, tb, ep);
+  else gemm_bf16_tc_kernel<true, true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta, tb, ep);
+  MMNAS_LAUNCH_CHECK();
+  return MMNAS_OK;
+}

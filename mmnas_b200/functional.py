@@ -1,0 +1,393 @@
+"""Block-level autograd Functions of the operator hot path.
+
+Each candidate block (SA / GA / RSA / FFN, reference mmnas/model/modules.py:248-362) is ONE autograd node whose
+forward and backward are fixed sequences of C-ABI kernel calls (mmnas_b200.kernels) — no torch arithmetic.
+Two arms:
+  fp32  FFMA GEMMs + fp32 attention                      (parity gate 1e-5 normwise)
+  bf16  tcgen05 GEMMs on bf16 operands, fp32 accumulate,  (parity gate 2e-2 normwise)
+        fp32 softmax / LayerNorm / geometry statistics
+The residual stream (block inputs/outputs) is fp32 in both arms; the bf16 arm additionally emits a bf16
+shadow of each block output so the next block's GEMM reads it without a cast pass.
+"""
+import math
+
+import torch
+from torch.autograd import Function
+
+from . import kernels as K
+from ._lib import require_cuda
+
+HEAD = 64
+
+
+class BlockCfg:
+    """Non-tensor arguments of one block call."""
+
+    def __init__(self, precision, residual, eps, drops, kmask=None, x16=None, kv16=None, w16=None):
+        self.precision = precision      # 'fp32' | 'bf16'
+        self.residual = residual
+        self.eps = eps
+        self.drops = drops              # tuple of kernels.Drop, one per dropout site of the block
+        self.kmask = kmask              # uint8 [B, Nk] (1 = padded key) or None
+        self.x16, self.kv16 = x16, kv16 # optional bf16 shadows of the inputs
+        self.w16 = w16 or {}            # bf16 (fused) weight copies for the tensor-core arm
+
+
+def _split_k(M, N, K):
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    kb = (K + 63) // 64
+    s = max(1, min((2 * 148 + tiles - 1) // tiles, kb // 4 if kb >= 4 else 1))
+    return s
+
+
+def _empty(shape, dtype, dev):
+    return torch.empty(shape, dtype=dtype, device=dev)
+
+
+def _bf16(t, shadow):
+    if shadow is not None:
+        return shadow
+    return K.cast_bf16(t)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# attention blocks: SelfAtt / RelSelfAtt / GuidedAtt  (modules.py:248-325 over MHAtt :158-199, RelMHAtt :202-245)
+# ----------------------------------------------------------------------------------------------------------
+class AttBlockFn(Function):
+    """out = LN(x + dropout(merge(att(q(x), k(kv), v(kv)))));  kv=None means self-attention (kv is x)."""
+
+    @staticmethod
+    def forward(ctx, x, kv, Wq, Wk, Wv, Wm, a2, b2, rel, g4, Wy, by, Wr, br, cfg):
+        require_cuda(x, kv, Wq)
+        dev = x.device
+        x = x.contiguous()
+        B, Nq, H = x.shape
+        I = Wq.shape[0]
+        heads = I // HEAD
+        self_att = kv is None
+        kvt = x if self_att else kv.contiguous()
+        Nk = kvt.shape[1]
+        Mq, Mk = B * Nq, B * Nk
+        bf = cfg.precision == 'bf16'
+        adt = torch.bfloat16 if bf else torch.float32
+        d_att, d_out = cfg.drops
+        scale = 1.0 / math.sqrt(HEAD)
+
+        x16 = kv16 = None
+        if bf:
+            x16 = _bf16(x, cfg.x16)
+            kv16 = x16 if self_att else _bf16(kvt, cfg.kv16)
+        # --- projections
+        if self_att:
+            qkv = _empty((Mq, 3 * I), adt, dev)
+            q, k, v = qkv[:, :I], qkv[:, I:2 * I], qkv[:, 2 * I:]
+            kvb = None
+            if bf:
+                K.gemm_bf16(Mq, 3 * I, H, x16, H, 0, cfg.w16['qkv'], H, 0, qkv, 3 * I)
+            else:
+                for W, dst in ((Wq, q), (Wk, k), (Wv, v)):
+                    K.gemm_f32(Mq, I, H, x, H, 1, W, 1, H, dst, 3 * I)
+        else:
+            qkv = _empty((Mq, I), adt, dev)
+            kvb = _empty((Mk, 2 * I), adt, dev)
+            q, k, v = qkv, kvb[:, :I], kvb[:, I:]
+            if bf:
+                K.gemm_bf16(Mq, I, H, x16, H, 0, cfg.w16['q'], H, 0, qkv, I)
+                K.gemm_bf16(Mk, 2 * I, H, kv16, H, 0, cfg.w16['kv'], H, 0, kvb, 2 * I)
+            else:
+                K.gemm_f32(Mq, I, H, x, H, 1, Wq, 1, H, q, I)
+                K.gemm_f32(Mk, I, H, kvt, H, 1, Wk, 1, H, k, 2 * I)
+                K.gemm_f32(Mk, I, H, kvt, H, 1, Wv, 1, H, v, 2 * I)
+        # --- RSA logit bias from the geometry path (fp32 in both arms)
+        bias = None
+        R = 0
+        if Wr is not None:
+            R = Wr.shape[1]
+            bias = _empty((B, heads, Nq, Nk), torch.float32, dev)
+            if g4 is not None:
+                K.relbias_fwd(B, Nq, heads, R, None, g4.contiguous(), Wy, by, Wr, br, bias)
+            else:
+                rel = rel.contiguous()
+                K.relbias_fwd(B, Nq, heads, R, rel, None, None, None, Wr, br, bias)
+        # --- attention core
+        atted = _empty((Mq, I), adt, dev)
+        K.attn_fwd(B, heads, Nq, Nk, q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+                   cfg.kmask, bias, atted, I, scale, d_att)
+        # --- merge projection, residual, LayerNorm
+        branch = _empty((Mq, H), torch.float32, dev)
+        if bf:
+            K.gemm_bf16(Mq, H, I, atted, I, 0, cfg.w16['m'], I, 0, branch, H)
+        else:
+            K.gemm_f32(Mq, H, I, atted, I, 1, Wm, 1, I, branch, H)
+        out = _empty((B, Nq, H), torch.float32, dev)
+        out16 = _empty((B, Nq, H), torch.bfloat16, dev) if bf else None
+        norm = a2 is not None
+        mean = _empty((Mq,), torch.float32, dev) if norm else None
+        sigma = _empty((Mq,), torch.float32, dev) if norm else None
+        K.ln_residual_fwd(Mq, H, x if cfg.residual else None, branch, a2, b2, cfg.eps, out, out16, mean, sigma, d_out)
+
+        ctx.cfg, ctx.dims = cfg, (B, Nq, Nk, H, I, heads, R, self_att)
+        ctx.save_for_backward(x, kvt, Wq, Wk, Wv, Wm, a2, rel, g4, Wy, by, Wr, br, qkv, kvb, bias, atted, branch, mean,
+                              sigma, x16, kv16)
+        if bf:
+            ctx.mark_non_differentiable(out16)
+            return out, out16
+        return out, None
+
+    @staticmethod
+    def backward(ctx, dout, _unused=None):
+        cfg = ctx.cfg
+        B, Nq, Nk, H, I, heads, R, self_att = ctx.dims
+        (x, kvt, Wq, Wk, Wv, Wm, a2, rel, g4, Wy, by, Wr, br, qkv, kvb, bias, atted, z, mean, sigma, x16,
+         kv16) = ctx.saved_tensors
+        dev = x.device
+        Mq, Mk = B * Nq, B * Nk
+        bf = cfg.precision == 'bf16'
+        adt = torch.bfloat16 if bf else torch.float32
+        d_att, d_out = cfg.drops
+        scale = 1.0 / math.sqrt(HEAD)
+        norm = a2 is not None
+        dout = dout.contiguous()
+
+        # --- LayerNorm + residual + output-dropout backward
+        dz = _empty((Mq, H), torch.float32, dev) if cfg.residual else None
+        separate = bf or d_out.active or not cfg.residual
+        dbranch = _empty((Mq, H), adt, dev) if separate else None
+        da2 = torch.zeros(H, dtype=torch.float32, device=dev) if norm else None
+        db2 = torch.zeros(H, dtype=torch.float32, device=dev) if norm else None
+        K.ln_residual_bwd(Mq, H, dout, z, mean, sigma, a2, cfg.eps, dz, dbranch, da2, db2, d_out)
+        if dbranch is None:
+            dbranch = dz
+        # --- merge projection backward
+        datt = _empty((Mq, I), adt, dev)
+        if bf:
+            dWm = torch.zeros((H, I), dtype=torch.float32, device=dev)
+            K.gemm_bf16(H, I, Mq, dbranch, H, 1, atted, I, 1, dWm, I, split_k=_split_k(H, I, Mq))
+            K.gemm_bf16(Mq, I, H, dbranch, H, 0, cfg.w16['m'], I, 1, datt, I)
+        else:
+            dWm = _empty((H, I), torch.float32, dev)
+            K.gemm_f32(H, I, Mq, dbranch, 1, H, atted, I, 1, dWm, I)
+            K.gemm_f32(Mq, I, H, dbranch, H, 1, Wm, I, 1, datt, I)
+        # --- attention core backward
+        if self_att:
+            q, k, v = qkv[:, :I], qkv[:, I:2 * I], qkv[:, 2 * I:]
+            dqkv = _empty((Mq, 3 * I), adt, dev)
+            dq, dk, dv = dqkv[:, :I], dqkv[:, I:2 * I], dqkv[:, 2 * I:]
+            dkvb = None
+        else:
+            q, k, v = qkv, kvb[:, :I], kvb[:, I:]
+            dqkv = _empty((Mq, I), adt, dev)
+            dkvb = _empty((Mk, 2 * I), adt, dev)
+            dq, dk, dv = dqkv, dkvb[:, :I], dkvb[:, I:]
+        dbias = _empty((B, heads, Nq, Nk), torch.float32, dev) if bias is not None else None
+        K.attn_bwd(B, heads, Nq, Nk, q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+                   cfg.kmask, bias, atted, I, datt, I, dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0),
+                   dv.data_ptr(), dv.stride(0), dbias, scale, d_att)
+        # --- geometry-bias backward
+        drel = dWy = dby = dWr = dbr = None
+        if bias is not None:
+            dWr = torch.zeros_like(Wr)
+            dbr = torch.zeros_like(br)
+            if g4 is not None:
+                dWy = torch.zeros_like(Wy)
+                dby = torch.zeros_like(by)
+                K.relbias_bwd(B, Nq, heads, R, None, g4, Wy, by, Wr, br, dbias, None, dWy, dby, dWr, dbr)
+            else:
+                drel = torch.empty_like(rel)
+                K.relbias_bwd(B, Nq, heads, R, rel, None, None, None, Wr, br, dbias, drel, None, None, dWr, dbr)
+        # --- projection backward: weight gradients and input gradients
+        dkv_in = None
+        if self_att:
+            if bf:
+                dW = torch.zeros((3 * I, H), dtype=torch.float32, device=dev)
+                K.gemm_bf16(3 * I, H, Mq, dqkv, 3 * I, 1, x16, H, 1, dW, H, split_k=_split_k(3 * I, H, Mq))
+                if dz is None:
+                    dz = _empty((Mq, H), torch.float32, dev)
+                    K.gemm_bf16(Mq, H, 3 * I, dqkv, 3 * I, 0, cfg.w16['qkv'], H, 1, dz, H)
+                else:
+                    K.gemm_bf16(Mq, H, 3 * I, dqkv, 3 * I, 0, cfg.w16['qkv'], H, 1, dz, H, accumulate=True)
+            else:
+                dW = _empty((3 * I, H), torch.float32, dev)
+                K.gemm_f32(3 * I, H, Mq, dqkv, 1, 3 * I, x, H, 1, dW, H)
+                acc = dz is not None
+                if dz is None:
+                    dz = _empty((Mq, H), torch.float32, dev)
+                for W, d in ((Wq, dq), (Wk, dk), (Wv, dv)):
+                    K.gemm_f32(Mq, H, I, d, 3 * I, 1, W, H, 1, dz, H, accumulate=acc)
+                    acc = True
+            dWq, dWk, dWv = dW[:I], dW[I:2 * I], dW[2 * I:]
+        else:
+            dkv_in = _empty((Mk, H), torch.float32, dev)
+            if bf:
+                dWq = torch.zeros((I, H), dtype=torch.float32, device=dev)
+                dWkv = torch.zeros((2 * I, H), dtype=torch.float32, device=dev)
+                K.gemm_bf16(I, H, Mq, dqkv, I, 1, x16, H, 1, dWq, H, split_k=_split_k(I, H, Mq))
+                K.gemm_bf16(2 * I, H, Mk, dkvb, 2 * I, 1, kv16, H, 1, dWkv, H, split_k=_split_k(2 * I, H, Mk))
+                if dz is None:
+                    dz = _empty((Mq, H), torch.float32, dev)
+                    K.gemm_bf16(Mq, H, I, dqkv, I, 0, cfg.w16['q'], H, 1, dz, H)
+                else:
+                    K.gemm_bf16(Mq, H, I, dqkv, I, 0, cfg.w16['q'], H, 1, dz, H, accumulate=True)
+                K.gemm_bf16(Mk, H, 2 * I, dkvb, 2 * I, 0, cfg.w16['kv'], H, 1, dkv_in, H)
+            else:
+                dWq = _empty((I, H), torch.float32, dev)
+                dWkv = _empty((2 * I, H), torch.float32, dev)
+                K.gemm_f32(I, H, Mq, dqkv, 1, I, x, H, 1, dWq, H)
+                K.gemm_f32(2 * I, H, Mk, dkvb, 1, 2 * I, kvt, H, 1, dWkv, H)
+                acc = dz is not None
+                if dz is None:
+                    dz = _empty((Mq, H), torch.float32, dev)
+                K.gemm_f32(Mq, H, I, dq, I, 1, Wq, H, 1, dz, H, accumulate=acc)
+                K.gemm_f32(Mk, H, I, dk, 2 * I, 1, Wk, H, 1, dkv_in, H)
+                K.gemm_f32(Mk, H, I, dv, 2 * I, 1, Wv, H, 1, dkv_in, H, accumulate=True)
+            dWk, dWv = dWkv[:I], dWkv[I:]
+            dkv_in = dkv_in.view(B, Nk, H)
+        return (dz.view(B, Nq, H), dkv_in, dWq, dWk, dWv, dWm, da2, db2, drel, None, dWy, dby, dWr, dbr, None)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# FeedForward  (modules.py:328-362 over MLP :34-41 / FC :13-31)
+# ----------------------------------------------------------------------------------------------------------
+class FFNBlockFn(Function):
+    """out = LN(x + dropout(W2 dropout(relu(W1 x + b1)) + b2))"""
+
+    @staticmethod
+    def forward(ctx, x, W1, b1, W2, b2f, a2, b2, cfg):
+        require_cuda(x, W1)
+        dev = x.device
+        x = x.contiguous()
+        B, N, H = x.shape
+        Fd = W1.shape[0]
+        M = B * N
+        bf = cfg.precision == 'bf16'
+        adt = torch.bfloat16 if bf else torch.float32
+        d_mid, d_out = cfg.drops
+        x16 = _bf16(x, cfg.x16) if bf else None
+        h = _empty((M, Fd), adt, dev)
+        branch = _empty((M, H), torch.float32, dev)
+        if bf:
+            K.gemm_bf16(M, Fd, H, x16, H, 0, cfg.w16['w1'], H, 0, h, Fd, bias=b1, relu=True, drop=d_mid)
+            K.gemm_bf16(M, H, Fd, h, Fd, 0, cfg.w16['w2'], Fd, 0, branch, H, bias=b2f)
+        else:
+            K.gemm_f32(M, Fd, H, x, H, 1, W1, 1, H, h, Fd, bias=b1, epilogue=2 if d_mid.active else 1, drop=d_mid)
+            K.gemm_f32(M, H, Fd, h, Fd, 1, W2, 1, Fd, branch, H, bias=b2f)
+        out = _empty((B, N, H), torch.float32, dev)
+        out16 = _empty((B, N, H), torch.bfloat16, dev) if bf else None
+        norm = a2 is not None
+        mean = _empty((M,), torch.float32, dev) if norm else None
+        sigma = _empty((M,), torch.float32, dev) if norm else None
+        K.ln_residual_fwd(M, H, x if cfg.residual else None, branch, a2, b2, cfg.eps, out, out16, mean, sigma, d_out)
+        ctx.cfg, ctx.dims = cfg, (B, N, H, Fd)
+        ctx.save_for_backward(x, W1, W2, a2, h, branch, mean, sigma, x16)
+        if bf:
+            ctx.mark_non_differentiable(out16)
+            return out, out16
+        return out, None
+
+    @staticmethod
+    def backward(ctx, dout, _unused=None):
+        cfg = ctx.cfg
+        B, N, H, Fd = ctx.dims
+        x, W1, W2, a2, h, z, mean, sigma, x16 = ctx.saved_tensors
+        dev = x.device
+        M = B * N
+        bf = cfg.precision == 'bf16'
+        adt = torch.bfloat16 if bf else torch.float32
+        d_mid, d_out = cfg.drops
+        norm = a2 is not None
+        dout = dout.contiguous()
+        dz = _empty((M, H), torch.float32, dev) if cfg.residual else None
+        separate = bf or d_out.active or not cfg.residual
+        dbranch = _empty((M, H), adt, dev) if separate else None
+        da2 = torch.zeros(H, dtype=torch.float32, device=dev) if norm else None
+        db2 = torch.zeros(H, dtype=torch.float32, device=dev) if norm else None
+        K.ln_residual_bwd(M, H, dout, z, mean, sigma, a2, cfg.eps, dz, dbranch, da2, db2, d_out)
+        if dbranch is None:
+            dbranch = dz
+        keep_scale = 1.0 / (1.0 - d_mid.p) if d_mid.active else 1.0
+        dbias2 = _empty((H,), torch.float32, dev)
+        dbias1 = _empty((Fd,), torch.float32, dev)
+        dh = _empty((M, Fd), adt, dev)
+        K.colsum(dbranch, M, H, H, dbias2)
+        if bf:
+            dW2 = torch.zeros((H, Fd), dtype=torch.float32, device=dev)
+            dW1 = torch.zeros((Fd, H), dtype=torch.float32, device=dev)
+            K.gemm_bf16(H, Fd, M, dbranch, H, 1, h, Fd, 1, dW2, Fd, split_k=_split_k(H, Fd, M))
+            K.gemm_bf16(M, Fd, H, dbranch, H, 0, cfg.w16['w2'], Fd, 1, dh, Fd, aux=h, ld_aux=Fd, aux_scale=keep_scale)
+            K.colsum(dh, M, Fd, Fd, dbias1)
+            K.gemm_bf16(Fd, H, M, dh, Fd, 1, x16, H, 1, dW1, H, split_k=_split_k(Fd, H, M))
+            if dz is None:
+                dz = _empty((M, H), torch.float32, dev)
+                K.gemm_bf16(M, H, Fd, dh, Fd, 0, cfg.w16['w1'], H, 1, dz, H)
+            else:
+                K.gemm_bf16(M, H, Fd, dh, Fd, 0, cfg.w16['w1'], H, 1, dz, H, accumulate=True)
+        else:
+            dW2 = _empty((H, Fd), torch.float32, dev)
+            dW1 = _empty((Fd, H), torch.float32, dev)
+            K.gemm_f32(H, Fd, M, dbranch, 1, H, h, Fd, 1, dW2, Fd)
+            K.gemm_f32(M, Fd, H, dbranch, H, 1, W2, Fd, 1, dh, Fd, epilogue=3, aux=h, ld_aux=Fd, aux_scale=keep_scale)
+            K.colsum(dh, M, Fd, Fd, dbias1)
+            K.gemm_f32(Fd, H, M, dh, 1, Fd, x, H, 1, dW1, H)
+            acc = dz is not None
+            if dz is None:
+                dz = _empty((M, H), torch.float32, dev)
+            K.gemm_f32(M, H, Fd, dh, Fd, 1, W1, H, 1, dz, H, accumulate=acc)
+        return dz.view(B, N, H), dW1, dbias1, dW2, dbias2, da2, db2, None
+
+
+# ----------------------------------------------------------------------------------------------------------
+# stand-alone LayerNorm (modules.py:44-56) — same kernel with no residual / dropout
+# ----------------------------------------------------------------------------------------------------------
+class LayerNormFn(Function):
+    @staticmethod
+    def forward(ctx, x, a2, b2, eps):
+        require_cuda(x)
+        shape = x.shape
+        H = shape[-1]
+        z = x.reshape(-1, H).to(torch.float32).clone(memory_format=torch.contiguous_format)
+        rows = z.shape[0]
+        out = torch.empty_like(z)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        sigma = torch.empty(rows, dtype=torch.float32, device=x.device)
+        K.ln_residual_fwd(rows, H, None, z, a2, b2, eps, out, None, mean, sigma)
+        ctx.save_for_backward(z, mean, sigma, a2)
+        ctx.eps, ctx.shape = eps, shape
+        return out.view(shape)
+
+    @staticmethod
+    def backward(ctx, dout):
+        z, mean, sigma, a2 = ctx.saved_tensors
+        rows, H = z.shape
+        dout = dout.reshape(rows, H).contiguous()
+        dz = torch.empty_like(z)
+        da2 = torch.zeros_like(a2)
+        db2 = torch.zeros_like(a2)
+        K.ln_residual_bwd(rows, H, dout, z, mean, sigma, a2, ctx.eps, dz, None, da2, db2)
+        return dz.view(ctx.shape), da2, db2, None
+
+
+# ----------------------------------------------------------------------------------------------------------
+# supernet mixed-op, 'full' / 'two' modes  (mixed.py:60-68): out = sum_k gate_k * o_k, inactive o_k detached
+# ----------------------------------------------------------------------------------------------------------
+class MixedSumFn(Function):
+    """forward(gate, n_active, o_0 ... o_{K-1}) with the first n_active candidates taking gradient."""
+
+    @staticmethod
+    def forward(ctx, gate, n_active, *outs):
+        require_cuda(gate, *outs)
+        outs = [o.contiguous() for o in outs]
+        out = torch.empty_like(outs[0])
+        K.mixed_accum(outs, gate, out)
+        ctx.n_active = n_active
+        ctx.save_for_backward(gate, *outs)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        gate, *outs = ctx.saved_tensors
+        dout = dout.contiguous()
+        gate_grad = torch.empty(len(outs), dtype=torch.float32, device=gate.device)
+        d_outs = [torch.empty_like(o) if (i < ctx.n_active and ctx.needs_input_grad[2 + i]) else None
+                  for i, o in enumerate(outs)]
+        K.mixed_alpha_dot(outs, gate, dout, gate_grad, d_outs)
+        return (gate_grad, None) + tuple(d_outs)

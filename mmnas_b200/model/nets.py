@@ -1,0 +1,267 @@
+"""Callers of the operator hot path: cells, backbones and the task nets (train-time `Net_Full`, search-time
+`Net_Search`), mirroring mmnas/model/full_{vqa,vgd,itm}.py and hygr_{vqa,vgd,itm}.py.
+
+Only the 30-node backbone is the CUDA hot path; stem (embedding, LSTM, imgfeat_linear, masks) and task heads
+(AttFlat, projections) are the adjacent rows of SURVEY §8f and stay on PyTorch for now.  Module names,
+creation order (=> identical default init under one seed) and state-dict keys follow the reference, incl. its
+`backnone` spelling, so reference checkpoints load with load_state_dict.
+
+The one deliberate difference: RSA blocks receive a `RelGeometry` handle (raw 4-d geometry + the
+`linear_y_rel` layer) instead of the dense relu(linear_y_rel(g)) [B,N,N,64] tensor, unless
+`rel_mode='dense'` is requested.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .mixed import MixedOp
+from .modules import AttFlat, LayerNorm, RelGeometry
+from ..utils.ops_adapter import OpsAdapter
+
+OPS_ADAPTER = OpsAdapter()
+
+
+def _chain(rows, s, pre, s_mask, pre_mask, rel_embed):
+    """Cell forward (full_vqa.py:24-28 / hygr_vqa.py:23-27): every node is the sum over its row of ops; the
+    single-op rows of every shipped arch skip the `0 + x` add so the bf16 shadow of x survives."""
+    for ops in rows:
+        if len(ops) == 1:
+            s = ops[0](s, pre, s_mask, pre_mask, rel_embed)
+        else:
+            s = sum(op(s, pre, s_mask, pre_mask, rel_embed) for op in ops)
+    return s
+
+
+class Cell_Full(nn.Module):
+    def __init__(self, __C, type):
+        super().__init__()
+        self.dag = nn.ModuleList(
+            nn.ModuleList(OPS_ADAPTER.OPS[name](__C, norm=__C.OPS_NORM, residual=__C.OPS_RESIDUAL) for name in node)
+            for node in __C.GENOTYPE[type])
+        self.NODES = len(self.dag)
+
+    def forward(self, s, pre=None, s_mask=None, pre_mask=None, rel_embed=None):
+        return _chain(self.dag, s, pre, s_mask, pre_mask, rel_embed)
+
+
+class Cell_Search(nn.Module):
+    def __init__(self, __C, type):
+        super().__init__()
+        self.dag = nn.ModuleList(nn.ModuleList([MixedOp(__C, type + '_safe')]) for _ in range(__C.NODES[type]))
+
+    def forward(self, s, pre=None, s_mask=None, pre_mask=None, rel_embed=None):
+        return _chain(self.dag, s, pre, s_mask, pre_mask, rel_embed)
+
+
+class _Backbone(nn.Module):
+    CELL = None
+
+    def __init__(self, __C):
+        super().__init__()
+        self.cells_enc = nn.ModuleList(self.CELL(__C, type='enc') for _ in range(__C.LAYERS))
+        self.cells_dec = nn.ModuleList(self.CELL(__C, type='dec') for _ in range(__C.LAYERS))
+
+    def forward(self, x, y, x_mask, y_mask, x_rel_embed, y_rel_embed):
+        for cell in self.cells_enc:
+            x = cell(s=x, s_mask=x_mask, rel_embed=x_rel_embed)
+        for cell in self.cells_dec:
+            y = cell(s=y, pre=x, s_mask=y_mask, pre_mask=x_mask, rel_embed=y_rel_embed)
+        return x, y
+
+
+class Backbone_Full(_Backbone):
+    CELL = Cell_Full
+
+
+class Backbone_Search(_Backbone):
+    CELL = Cell_Search
+
+
+def make_mask(feature):
+    return (torch.sum(torch.abs(feature), dim=-1) == 0).unsqueeze(1).unsqueeze(2)
+
+
+class _NetBase(nn.Module):
+    """Stem shared by the three tasks and by Net_Full / Net_Search."""
+    BACKBONE = None
+    SEARCH = False
+
+    def __init__(self, __C, init_dict, task='vqa', rel_mode='geometry'):
+        super().__init__()
+        assert task in ('vqa', 'vgd', 'itm') and rel_mode in ('geometry', 'dense')
+        self.task, self.rel_mode = task, rel_mode
+        self.BBOX_FEATURE = __C.BBOX_FEATURE
+        self.SCORES_LOSS = getattr(__C, 'SCORES_LOSS', None)
+        self.embedding = nn.Embedding(num_embeddings=init_dict['token_size'], embedding_dim=__C.WORD_EMBED_SIZE)
+        self.embedding.weight.data.copy_(torch.from_numpy(init_dict['pretrained_emb']))
+        self.lstm = nn.LSTM(input_size=__C.WORD_EMBED_SIZE, hidden_size=__C.HSIZE, num_layers=1, batch_first=True)
+        feat = __C.FRCNFEAT_SIZE
+        if __C.BBOX_FEATURE:
+            self.bboxfeat_linear = nn.Linear(5, __C.BBOXFEAT_EMB_SIZE)
+            feat += __C.BBOXFEAT_EMB_SIZE
+        self.imgfeat_linear = nn.Linear(feat, __C.HSIZE)
+        self.backnone = self.BACKBONE(__C)
+        self.attflat_x = AttFlat(__C)
+        if task == 'vgd':       # full_vgd.py:83-87
+            self.attfc_y = nn.Linear(__C.HSIZE, __C.ATTFLAT_OUT_SIZE)
+            self.proj_norm = LayerNorm(__C.ATTFLAT_OUT_SIZE)
+            self.proj_scores = nn.Linear(__C.ATTFLAT_OUT_SIZE, 1)
+            self.proj_reg = nn.Linear(__C.ATTFLAT_OUT_SIZE, 4)
+        else:                   # full_vqa.py:78-80, full_itm.py (proj -> 1 logit)
+            self.attflat_y = AttFlat(__C)
+            self.proj_norm = LayerNorm(__C.ATTFLAT_OUT_SIZE)
+            self.proj = nn.Linear(__C.ATTFLAT_OUT_SIZE, init_dict['ans_size'] if task == 'vqa' else 1)
+        if self.SEARCH:
+            self.linear_x_rel = nn.Linear(3, __C.REL_SIZE)
+        self.linear_y_rel = nn.Linear(4, __C.REL_SIZE)
+
+    def forward(self, input):
+        frcn_feat, bbox_feat, y_rel, ques_ix, x_rel = input
+        x_mask = make_mask(ques_ix.unsqueeze(2))
+        y_mask = make_mask(frcn_feat)
+        x_in, _ = self.lstm(self.embedding(ques_ix))
+        if self.BBOX_FEATURE:
+            frcn_feat = torch.cat((frcn_feat, self.bboxfeat_linear(bbox_feat)), dim=-1)
+        y_in = self.imgfeat_linear(frcn_feat)
+        # x_rel is never consumed (no relation op is an encoder candidate); the reference still embeds it in
+        # Net_Search (hygr_vqa.py:130) — the parameters exist here for checkpoint parity, the dead matmul does not run.
+        if self.rel_mode == 'geometry':
+            y_rel = RelGeometry(y_rel, self.linear_y_rel)
+        else:
+            y_rel = F.relu(self.linear_y_rel(y_rel))
+        x_out, y_out = self.backnone(x_in, y_in, x_mask, y_mask, x_rel, y_rel)
+        return self.head(x_out, y_out, x_mask, y_mask)
+
+    def head(self, x_out, y_out, x_mask, y_mask):
+        if self.task == 'vgd':      # full_vgd.py:105-112
+            xy = self.attflat_x(x_out, x_mask).unsqueeze(1) + self.attfc_y(y_out)
+            xy = self.proj_norm(xy)
+            scores = self.proj_scores(xy).squeeze(-1)
+            if self.SCORES_LOSS == 'kld':
+                scores = F.log_softmax(scores, dim=-1)
+            return scores, self.proj_reg(xy)
+        xy = self.proj_norm(self.attflat_x(x_out, x_mask) + self.attflat_y(y_out, y_mask))
+        out = self.proj(xy)
+        if self.task == 'itm':      # full_itm.py:109-110
+            out = torch.sigmoid(out.squeeze(-1))
+        return out
+
+    make_mask = staticmethod(make_mask)
+
+
+class Net_Full(_NetBase):
+    """Train-time net built from a genotype (arch/*.json entry in __C.GENOTYPE)."""
+    BACKBONE = Backbone_Full
+
+
+class Net_Search(_NetBase):
+    """Search-time supernet: one MixedOp per node + the architecture-parameter bookkeeping of hygr_vqa.py:124-297."""
+    BACKBONE = Backbone_Search
+    SEARCH = True
+    # MCAN-like prior written over the alpha init (hygr_vqa.py:142-156)
+    PRIOR_ENC = ['self_att_64', 'feed_forward'] * 6
+    PRIOR_DEC = ['rel_self_att_64', 'guided_att_64', 'feed_forward'] * 7
+
+    def __init__(self, __C, init_dict, task='vqa', rel_mode='geometry'):
+        super().__init__(__C, init_dict, task, rel_mode)
+        self._alpha_init_type = __C.ALPHA_INIT_TYPE
+        self._redundant_modules = None
+        self._unused_modules = None
+        self.init_arch()
+        self._net_weights = [(n, p) for n, p in self.named_parameters()
+                             if 'alpha_prob' not in n and 'alpha_gate' not in n]
+
+    # ---- architecture parameters ---------------------------------------------------------------------
+    def init_arch(self):
+        self._alphas_prob = [(n, p) for n, p in self.named_parameters() if 'alpha_prob' in n]
+        self._alphas_gate = [(n, p) for n, p in self.named_parameters() if 'alpha_gate' in n]
+        for _, p in self._alphas_prob:
+            if self._alpha_init_type == 'normal':
+                p.data.normal_(0, 1e-3)
+            elif self._alpha_init_type == 'uniform':
+                p.data.uniform_(-1e-3, 1e-3)
+        # The reference then overwrites the first 12 alphas with an encoder-sized prior and the rest with a
+        # decoder-sized one (so it assumes 12 encoder nodes, hygr_vqa.py:148); the same rule is applied here.
+        prior = self.PRIOR_ENC + self.PRIOR_DEC
+        for ix, (name, (_, p)) in enumerate(zip(prior, self._alphas_prob)):
+            cands = OPS_ADAPTER.Used_OPS['enc_safe' if ix < 12 else 'dec_safe']
+            init = np.full(len(cands), -1., dtype=np.float32)
+            init[cands.index(name)] = 1.
+            p.data = torch.from_numpy(init).to(p.device)
+
+    @property
+    def redundant_modules(self):
+        if self._redundant_modules is None:
+            self._redundant_modules = [m for m in self.modules() if str(m).startswith('MixedOp')]
+        return self._redundant_modules
+
+    def reset_binary_gates(self):
+        for m in self.redundant_modules:
+            m.binarize()
+
+    def unused_modules_off(self):
+        self._unused_modules = []
+        for m in self.redundant_modules:
+            involved = m.active_index + m.inactive_index if MixedOp.MODE in ('full', 'two', 'full_v2') else m.active_index
+            unused = {}
+            for i in range(m.n_choices):
+                if i not in involved:
+                    unused[i] = m.candidate_ops[i]
+                    m.candidate_ops[i] = None
+            self._unused_modules.append(unused)
+
+    def unused_modules_back(self):
+        if self._unused_modules is None:
+            return
+        for m, unused in zip(self.redundant_modules, self._unused_modules):
+            for i, op in unused.items():
+                m.candidate_ops[i] = op
+        self._unused_modules = None
+
+    def set_arch_param_grad(self):
+        for m in self.redundant_modules:
+            m.set_arch_param_grad()
+
+    def rescale_updated_arch_param(self):
+        for m in self.redundant_modules:
+            m.rescale_updated_arch_param()
+
+    def set_chosen_op_active(self):
+        for m in self.redundant_modules:
+            m.set_chosen_op_active()
+
+    def alpha_prob_parameters(self):
+        return (p for _, p in self._alphas_prob)
+
+    def alpha_gate_parameters(self):
+        return (p for _, p in self._alphas_gate)
+
+    def named_alpha_prob_parameters(self):
+        return iter(self._alphas_prob)
+
+    def named_alpha_gate_parameters(self):
+        return iter(self._alphas_gate)
+
+    def net_parameters(self):
+        return (p for _, p in self._net_weights)
+
+    def named_net_parameters(self):
+        return iter(self._net_weights)
+
+    # ---- genotype export (format of arch/*.json entries) -----------------------------------------------
+    def _alphas_of(self, kind):
+        return [p for n, p in self._alphas_prob if kind in n]
+
+    def parse(self, alpha_param_list, type):
+        return [[OPS_ADAPTER.Used_OPS[type][int(torch.topk(a, 1)[1][0])]] for a in alpha_param_list]
+
+    def genotype(self):
+        return {'enc': self.parse(self._alphas_of('enc'), 'enc'), 'dec': self.parse(self._alphas_of('dec'), 'dec')}
+
+    def parse_weights(self, alpha):
+        with torch.no_grad():
+            return [F.softmax(a, dim=-1).data.cpu().numpy() for a in alpha]
+
+    def genotype_weights(self):
+        return {'w_enc': self.parse_weights(self._alphas_of('enc')), 'w_dec': self.parse_weights(self._alphas_of('dec'))}

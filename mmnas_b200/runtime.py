@@ -1,0 +1,68 @@
+"""Process-wide runtime state of the operator path: precision mode and the dropout RNG state."""
+import itertools
+import threading
+
+import torch
+
+from . import kernels
+
+_PRECISION = 'bf16'          # 'fp32' (FFMA kernels, 1e-5 parity arm) | 'bf16' (tcgen05 arm, 2e-2)
+_rng_states = {}
+_salt_counter = itertools.count(1)
+_lock = threading.Lock()
+
+
+def set_precision(mode):
+    global _PRECISION
+    if mode not in ('fp32', 'bf16'):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    _PRECISION = mode
+
+
+def get_precision():
+    return _PRECISION
+
+
+class precision:
+    """Context manager: `with mmnas_b200.precision('fp32'): ...`"""
+
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = get_precision()
+        set_precision(self.mode)
+
+    def __exit__(self, *a):
+        set_precision(self.prev)
+
+
+def new_site():
+    """A process-unique id for one dropout site (one per module instance and per site inside it)."""
+    with _lock:
+        return next(_salt_counter)
+
+
+def rng_state(device):
+    """Device tensor {seed, step} (int64 bit patterns) driving every dropout site on `device`."""
+    key = torch.device(device)
+    if key.index is None:
+        key = torch.device('cuda', torch.cuda.current_device())
+    st = _rng_states.get(key)
+    if st is None:
+        seed = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
+        st = torch.tensor([seed, 0], dtype=torch.int64, device=key)
+        _rng_states[key] = st
+    return st
+
+
+def manual_seed(seed, device=None):
+    """Re-seed the dropout state of `device` (default: current CUDA device); the step counter restarts at 0."""
+    st = rng_state(device if device is not None else torch.device('cuda', torch.cuda.current_device()))
+    st.copy_(torch.tensor([int(seed) & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64))
+
+
+def advance(device=None):
+    """Bump the step counter: call once per training step (captured fine inside a CUDA graph)."""
+    st = rng_state(device if device is not None else torch.device('cuda', torch.cuda.current_device()))
+    kernels.rng_advance(st)

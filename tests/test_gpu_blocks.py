@@ -1,0 +1,195 @@
+"""Block-level parity on the B200: the drop-in operator classes (mmnas_b200.model.modules / mixed) against
+(1) the golden vectors produced by the unmodified reference and (2) the CPU oracle on seeded inputs at the
+BASELINE shapes.  fp32 arm: 1e-5 normwise; bf16 arm: 2e-2 normwise (north_star tolerances)."""
+import pytest
+import torch
+
+from oracle import mmnas_oracle as O
+from tests.util import load_golden, params_of, normwise
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+OPS4 = ['self_att_64', 'rel_self_att_64', 'guided_att_64', 'feed_forward']
+TOL = {'fp32': 1e-5, 'bf16': 2e-2}
+
+
+class Cfg:
+    def __init__(self, h, p=0.0):
+        self.HSIZE, self.DROPOUT_R, self.REL_SIZE, self.OPS_NORM, self.OPS_RESIDUAL = h, p, 64, True, True
+
+
+def build(name, h, state=None, norm=True, residual=True, p=0.0):
+    from mmnas_b200.utils.ops_adapter import OpsAdapter
+    op = OpsAdapter().OPS[name](Cfg(h, p), norm, residual)
+    if state is not None:
+        op.load_state_dict(state)
+    return op.to(DEV)
+
+
+def run_ours(op, mode, x, y, xm, ym, rel, gout):
+    import mmnas_b200
+    xs = [None if t is None else t.detach().to(DEV).requires_grad_(t.is_floating_point()) for t in (x, y)]
+    relc = rel
+    if torch.is_tensor(rel):
+        relc = rel.detach().to(DEV).requires_grad_(True)
+    with mmnas_b200.precision(mode):
+        out = op(xs[0], xs[1], None if xm is None else xm.to(DEV), None if ym is None else ym.to(DEV), relc)
+        out.backward(gout.to(DEV))
+    return out, xs[0].grad, (xs[1].grad if xs[1] is not None else None), (relc.grad if torch.is_tensor(relc) else None)
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+@pytest.mark.parametrize('name', OPS4)
+def test_block_matches_reference_golden(name, mode):
+    r = load_golden('ops_h128.npz', name)
+    op = build(name, 128, params_of(r))
+    out, gx, gy, grel = run_ours(op, mode, r['x'], r['y'], r['x_mask'], r['y_mask'], r['rel'], r['gout'])
+    tol = TOL[mode]
+    assert normwise(out, r['out']) < tol
+    assert normwise(gx, r['gx']) < tol
+    if 'gy' in r:
+        assert normwise(gy, r['gy']) < tol
+    if 'grel' in r:
+        assert normwise(grel, r['grel']) < tol
+    for n_, p_ in op.named_parameters():
+        assert normwise(p_.grad, r['g.' + n_]) < tol, n_
+
+
+def seeded_case(b, nx, ny, h, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(b, nx, h, generator=g)
+    y = torch.randn(b, ny, h, generator=g)
+    g4 = torch.randn(b, nx, nx, 4, generator=g)
+    xm = torch.zeros(b, 1, 1, nx, dtype=torch.bool)
+    ym = torch.zeros(b, 1, 1, ny, dtype=torch.bool)
+    for i in range(b):
+        lx = int(torch.randint(max(1, nx // 10), nx + 1, (1,), generator=g))
+        ly = int(torch.randint(1, ny + 1, (1,), generator=g))
+        xm[i, ..., lx:] = True
+        ym[i, ..., ly:] = True
+        g4[i, lx:] = 0
+        g4[i, :, lx:] = 0
+    gout = torch.randn(b, nx, h, generator=g)
+    return x, y, g4, xm, ym, gout
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+@pytest.mark.parametrize('h,nx,ny', [(512, 100, 14), (256, 100, 14), (512, 14, 100), (512, 36, 50), (512, 100, 15)])
+@pytest.mark.parametrize('name', OPS4)
+def test_block_matches_oracle_at_baseline_shapes(name, mode, h, nx, ny):
+    """VQA train (H=512, 100 regions x 14 tokens), VQA search (H=256), encoder side (14 tokens), ITM (36 x 50),
+    VGD (100 x 15).  RSA runs through the fused geometry path (RelGeometry)."""
+    from mmnas_b200.model.modules import RelGeometry
+    if name == 'rel_self_att_64' and nx < 36:
+        pytest.skip('relation attention only runs on the region side')
+    b = 4
+    x, y, g4, xm, ym, gout = seeded_case(b, nx, ny, h, seed=h + nx)
+    torch.manual_seed(888)
+    op = build(name, h)
+    lin = torch.nn.Linear(4, 64).to(DEV)
+    # oracle: float64 on CPU over the same weights
+    P = O.leaf_params({k: v.cpu() for k, v in op.state_dict().items()}, torch.float64)
+    Wy = lin.weight.detach().cpu().double().requires_grad_(True)
+    by = lin.bias.detach().cpu().double().requires_grad_(True)
+    xd, yd = x.double().requires_grad_(True), y.double().requires_grad_(True)
+    rel = torch.relu(torch.nn.functional.linear(g4.double(), Wy, by))
+    ref = O.op_forward(name, P, '', xd, yd, xm, ym, rel)
+    ref.backward(gout.double())
+    out, gx, gy, _ = run_ours(op, mode, x, y, xm, ym, RelGeometry(g4.to(DEV), lin), gout)
+    tol = TOL[mode]
+    assert normwise(out, ref) < tol
+    assert normwise(gx, xd.grad) < tol
+    if name == 'guided_att_64':
+        assert normwise(gy, yd.grad) < tol
+    for n_, p_ in op.named_parameters():
+        assert normwise(p_.grad, P[n_].grad) < tol, n_
+    if name == 'rel_self_att_64':
+        assert normwise(lin.weight.grad, Wy.grad) < tol
+        assert normwise(lin.bias.grad, by.grad) < tol
+
+
+@pytest.mark.parametrize('norm,residual', [(False, False), (True, False), (False, True)])
+@pytest.mark.parametrize('name', ['self_att_64', 'feed_forward'])
+def test_norm_and_residual_switches(name, norm, residual):
+    x, y, g4, xm, ym, gout = seeded_case(2, 20, 6, 128, seed=3)
+    torch.manual_seed(1)
+    op = build(name, 128, norm=norm, residual=residual)
+    P = O.leaf_params({k: v.cpu() for k, v in op.state_dict().items()}, torch.float64)
+    xd = x.double().requires_grad_(True)
+    ref = O.op_forward(name, P, '', xd, None, xm, None, None, norm=norm, residual=residual)
+    ref.backward(gout.double())
+    out, gx, _, _ = run_ours(op, 'fp32', x, None, xm, None, None, gout)
+    assert normwise(out, ref) < 1e-5
+    assert normwise(gx, xd.grad) < 1e-5
+    for n_, p_ in op.named_parameters():
+        assert normwise(p_.grad, P[n_].grad) < 1e-5, n_
+
+
+def test_padded_keys_do_not_influence_output():
+    """Size-independent property: values stored in padded key slots must not change any output row."""
+    import mmnas_b200
+    x, y, g4, xm, ym, gout = seeded_case(4, 100, 14, 512, seed=9)
+    torch.manual_seed(2)
+    op = build('guided_att_64', 512)
+    y2 = y.clone()
+    y2[ym.view(4, 14)] = 123.0
+    keep = ~ym.view(4, 14).all(1)                   # samples that have at least one valid key
+    with mmnas_b200.precision('bf16'), torch.no_grad():
+        a = op(x.to(DEV), y.to(DEV), None, ym.to(DEV))
+        b = op(x.to(DEV), y2.to(DEV), None, ym.to(DEV))
+    assert torch.equal(a[keep.to(DEV)], b[keep.to(DEV)])
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_mixed_op_full_mode_matches_reference_golden(mode):
+    import mmnas_b200
+    from mmnas_b200.model.mixed import MixedOp
+    r = load_golden('mixed_h64.npz')
+    m = MixedOp(Cfg(64), 'dec_safe')
+    m.load_state_dict(params_of(r))
+    m = m.to(DEV)
+    m.active_index, m.inactive_index = r['active'].tolist(), r['inactive'].tolist()
+    MixedOp.MODE = 'full'
+    try:
+        x = r['x'].to(DEV).requires_grad_(True)
+        y = r['y'].to(DEV).requires_grad_(True)
+        with mmnas_b200.precision(mode):
+            out = m(x, y, r['x_mask'].to(DEV), r['y_mask'].to(DEV), r['rel'].to(DEV))
+            out.backward(r['gout'].to(DEV))
+        m.set_arch_param_grad()
+    finally:
+        MixedOp.MODE = None
+    tol = TOL[mode]
+    assert normwise(out, r['out']) < tol
+    assert normwise(x.grad, r['gx']) < tol
+    assert normwise(m.alpha_gate.grad, r['gate_grad']) < tol
+    assert normwise(m.alpha_prob.grad, r['prob_grad']) < tol
+    a = m.active_index[0]
+    for n_, p_ in m.named_parameters():
+        if n_.startswith('candidate_ops.%d.' % a):
+            assert normwise(p_.grad, r['g.' + n_]) < tol, n_
+        elif n_.startswith('candidate_ops.'):
+            assert p_.grad is None, n_
+
+
+def test_training_dropout_is_unbiased_and_replayable():
+    """Dropout parity can only be statistical: the mean over many masks approaches the p=0 output,
+    and forward under an unchanged rng step is replayable (what the backward relies on)."""
+    import mmnas_b200
+    x, y, g4, xm, ym, gout = seeded_case(4, 100, 14, 256, seed=5)
+    torch.manual_seed(3)
+    op = build('feed_forward', 256, p=0.1)
+    op.train()
+    xd = x.to(DEV)
+    mmnas_b200.manual_seed(1)
+    with mmnas_b200.precision('fp32'), torch.no_grad():
+        op.eval()
+        clean = op(xd)
+        op.train()
+        outs = []
+        for _ in range(64):
+            mmnas_b200.advance()
+            outs.append(op(xd))
+        mean = torch.stack(outs).mean(0)
+    assert not torch.equal(outs[0], outs[1])
+    assert normwise(mean, clean) < 0.08

@@ -1,0 +1,315 @@
+"""Kernel-level parity tests, called through the C ABI (ctypes) on the B200.  Each kernel is compared with
+the same arithmetic written in float64 torch on identical seeded inputs (the per-kernel restatement of the
+reference lines cited in include/mmnas_b200.h); tolerances are normwise."""
+import math
+
+import pytest
+import torch
+
+from tests.util import normwise
+
+pytestmark = pytest.mark.gpu
+
+DEV = 'cuda'
+
+
+def K():
+    from mmnas_b200 import kernels
+    return kernels
+
+
+def rnd(*shape, seed=0, dtype=torch.float32, scale=1.0):
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+# ------------------------------------------------------------------------------------------ GEMM fp32
+@pytest.mark.parametrize('ta,tb', [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize('M,N,K_', [(200, 96, 130), (64, 64, 64), (37, 5, 11)])
+def test_gemm_f32_layouts(ta, tb, M, N, K_):
+    k = K()
+    A = rnd(K_, M, seed=1) if ta else rnd(M, K_, seed=1)
+    B = rnd(N, K_, seed=2) if tb else rnd(K_, N, seed=2)
+    bias = rnd(N, seed=3)
+    C = torch.empty(M, N, device=DEV)
+    a_rs, a_cs = (1, M) if ta else (K_, 1)
+    b_rs, b_cs = (1, K_) if tb else (N, 1)
+    k.gemm_f32(M, N, K_, A, a_rs, a_cs, B, b_rs, b_cs, C, N, bias=bias, epilogue=1)
+    Ad = (A.t() if ta else A).double()
+    Bd = (B.t() if tb else B).double()
+    ref = torch.relu(Ad @ Bd + bias.double())
+    assert normwise(C, ref) < 2e-6
+    # accumulate + aux-mask epilogue
+    aux = rnd(M, N, seed=4)
+    C2 = C.clone()
+    k.gemm_f32(M, N, K_, A, a_rs, a_cs, B, b_rs, b_cs, C2, N, epilogue=3, accumulate=True, aux=aux, ld_aux=N, aux_scale=1.25)
+    ref2 = ref + torch.where(aux.double() > 0, (Ad @ Bd) * 1.25, torch.zeros_like(ref))
+    assert normwise(C2, ref2) < 2e-6
+
+
+# ------------------------------------------------------------------------------------------ GEMM bf16 (tcgen05)
+@pytest.mark.parametrize('a_mn,b_mn', [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize('M,N,K_', [(128, 128, 64), (200, 256, 192), (896, 512, 512), (300, 96, 1000)])
+def test_gemm_bf16_layouts(a_mn, b_mn, M, N, K_):
+    k = K()
+    Kp = (K_ + 7) // 8 * 8
+    Mp = (M + 7) // 8 * 8
+    A = rnd(Kp if a_mn else M, Mp if a_mn else Kp, seed=1, dtype=torch.bfloat16)
+    B = rnd(Kp if b_mn else N, N if b_mn else Kp, seed=2, dtype=torch.bfloat16)
+    Ad = (A[:K_, :M].t() if a_mn else A[:, :K_]).double()
+    Bd = (B[:K_] if b_mn else B[:, :K_].t()).double()
+    ref = Ad @ Bd
+    C = torch.full((M, N), float('nan'), device=DEV)
+    k.gemm_bf16(M, N, K_, A, A.stride(0), a_mn, B, B.stride(0), b_mn, C, N)
+    assert normwise(C, ref) < 1e-5
+    # split-K accumulates into a zeroed fp32 buffer
+    C3 = torch.zeros(M, N, device=DEV)
+    k.gemm_bf16(M, N, K_, A, A.stride(0), a_mn, B, B.stride(0), b_mn, C3, N, split_k=3)
+    assert normwise(C3, ref) < 1e-5
+
+
+def test_gemm_bf16_epilogues():
+    k = K()
+    M, N, K_ = 333, 256, 512
+    A = rnd(M, K_, seed=1, dtype=torch.bfloat16)
+    B = rnd(N, K_, seed=2, dtype=torch.bfloat16)
+    bias = rnd(N, seed=3)
+    ref = A.double() @ B.double().t()
+    out16 = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    k.gemm_bf16(M, N, K_, A, K_, 0, B, K_, 0, out16, N, bias=bias, relu=True)
+    assert normwise(out16, torch.relu(ref + bias.double())) < 6e-3
+    aux = rnd(M, N, seed=4, dtype=torch.bfloat16)
+    k.gemm_bf16(M, N, K_, A, K_, 0, B, K_, 0, out16, N, aux=aux, ld_aux=N, aux_scale=0.5)
+    assert normwise(out16, torch.where(aux.double() > 0, ref * 0.5, torch.zeros_like(ref))) < 6e-3
+    C = rnd(M, N, seed=5)
+    ref_acc = C.double() + ref
+    k.gemm_bf16(M, N, K_, A, K_, 0, B, K_, 0, C, N, accumulate=True)
+    assert normwise(C, ref_acc) < 1e-5
+    # column-slice output (pitch > N), as used for the fused QKV buffer
+    big = torch.zeros(M, 3 * N, device=DEV, dtype=torch.bfloat16)
+    k.gemm_bf16(M, N, K_, A, K_, 0, B, K_, 0, big[:, N:2 * N], 3 * N)
+    assert normwise(big[:, N:2 * N], ref) < 6e-3
+    assert float(big[:, :N].abs().max()) == 0 and float(big[:, 2 * N:].abs().max()) == 0
+
+
+def test_gemm_bf16_dropout_matches_fp32_arm_mask():
+    """Both arms hash (row*N+col) with the same key, so they drop the same elements."""
+    k = K()
+    M, N, K_ = 256, 128, 64
+    A = torch.ones(M, K_, device=DEV)
+    B = torch.ones(N, K_, device=DEV)
+    st = torch.tensor([1234, 7], dtype=torch.int64, device=DEV)
+    d = k.Drop(st, salt=99, p=0.1)
+    C32 = torch.empty(M, N, device=DEV)
+    k.gemm_f32(M, N, K_, A, K_, 1, B, 1, K_, C32, N, epilogue=2, drop=d)
+    C16 = torch.empty(M, N, device=DEV)
+    k.gemm_bf16(M, N, K_, A.bfloat16(), K_, 0, B.bfloat16(), K_, 0, C16, N, relu=True, drop=d)
+    assert torch.equal(C32 == 0, C16 == 0)
+    frac = float((C32 == 0).float().mean())
+    assert abs(frac - 0.1) < 0.01
+    kept = C32[C32 != 0]
+    assert torch.allclose(kept, torch.full_like(kept, K_ / 0.9), rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------ LayerNorm tail
+@pytest.mark.parametrize('rows,H', [(7, 64), (896, 512), (301, 256), (5, 1024)])
+@pytest.mark.parametrize('residual', [True, False])
+def test_ln_residual_fwd_bwd(rows, H, residual):
+    k = K()
+    x, br = rnd(rows, H, seed=1), rnd(rows, H, seed=2)
+    a2, b2 = 1 + 0.1 * rnd(H, seed=3), 0.1 * rnd(H, seed=4)
+    go = rnd(rows, H, seed=5)
+    xd, bd, ad, bbd = (t.double().requires_grad_(True) for t in (x, br, a2, b2))
+    z = xd + bd if residual else bd
+    mu = z.mean(-1, keepdim=True)
+    ref = ad * (z - mu) / (z.std(-1, keepdim=True) + 1e-6) + bbd
+    ref.backward(go.double())
+    out = torch.empty(rows, H, device=DEV)
+    out16 = torch.empty(rows, H, device=DEV, dtype=torch.bfloat16)
+    mean, sigma = torch.empty(rows, device=DEV), torch.empty(rows, device=DEV)
+    zbuf = br.clone()
+    k.ln_residual_fwd(rows, H, x if residual else None, zbuf, a2, b2, 1e-6, out, out16, mean, sigma)
+    assert normwise(out, ref) < 2e-6
+    assert normwise(out16, ref) < 5e-3
+    assert normwise(zbuf, z) < 1e-6
+    dz = torch.empty(rows, H, device=DEV)
+    da, db = torch.zeros(H, device=DEV), torch.zeros(H, device=DEV)
+    k.ln_residual_bwd(rows, H, go, zbuf, mean, sigma, a2, 1e-6, dz, None, da, db)
+    assert normwise(dz, bd.grad) < 5e-6
+    assert normwise(da, ad.grad) < 5e-6
+    assert normwise(db, bbd.grad) < 5e-6
+
+
+def test_ln_norm_off_and_dropout_consistency():
+    k = K()
+    rows, H = 64, 256
+    x, br, go = rnd(rows, H, seed=1), torch.ones(rows, H, device=DEV), rnd(rows, H, seed=2)
+    st = torch.tensor([5, 0], dtype=torch.int64, device=DEV)
+    d = k.Drop(st, salt=3, p=0.25)
+    out = torch.empty(rows, H, device=DEV)
+    zbuf = br.clone()
+    k.ln_residual_fwd(rows, H, x, zbuf, None, None, 1e-6, out, None, None, None, drop=d)
+    mult = out - x                       # = dropout multiplier (branch was all ones)
+    assert all(min(abs(u), abs(u - 1 / 0.75)) < 2e-3 for u in torch.unique(mult.round(decimals=3)).tolist())
+    assert abs(float((mult == 0).float().mean()) - 0.25) < 0.02
+    dz = torch.empty(rows, H, device=DEV)
+    dbr = torch.empty(rows, H, device=DEV)
+    k.ln_residual_bwd(rows, H, go, None, None, None, None, 1e-6, dz, dbr, None, None, drop=d)
+    assert torch.equal(dz, go)
+    assert torch.allclose(dbr, go * mult, rtol=1e-5, atol=1e-6)   # backward regenerates the same mask
+
+
+# ------------------------------------------------------------------------------------------ attention core
+def attn_ref(q, k, v, mask, bias, scale):
+    B, Nq, I = q.shape
+    h = I // 64
+    qh, kh, vh = (t.view(B, -1, h, 64).transpose(1, 2) for t in (q, k, v))
+    s = qh @ kh.transpose(-2, -1) * scale
+    if bias is not None:
+        s = bias + s
+    if mask is not None:
+        s = s.masked_fill(mask.view(B, 1, 1, -1).bool(), -1e9)
+    p = torch.softmax(s, -1)
+    return (p @ vh).transpose(1, 2).reshape(B, Nq, I)
+
+
+@pytest.mark.parametrize('B,h,Nq,Nk,with_bias', [(2, 2, 7, 7, True), (3, 8, 100, 100, True), (3, 8, 100, 14, False),
+                                                  (2, 4, 36, 50, False), (1, 1, 100, 128, False)])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_attention_fwd_bwd(B, h, Nq, Nk, with_bias, dtype):
+    k = K()
+    I = 64 * h
+    q, kk, v = rnd(B, Nq, I, seed=1, dtype=dtype), rnd(B, Nk, I, seed=2, dtype=dtype), rnd(B, Nk, I, seed=3, dtype=dtype)
+    go = rnd(B, Nq, I, seed=4, dtype=dtype)
+    mask = torch.zeros(B, Nk, dtype=torch.uint8, device=DEV)
+    mask[0, Nk // 2:] = 1
+    mask[B - 1, :] = 1                      # fully padded sample -> uniform attention
+    bias = rnd(B, h, Nq, Nk, seed=5) if with_bias else None
+    qd, kd, vd = (t.double().requires_grad_(True) for t in (q, kk, v))
+    bd = bias.double().requires_grad_(True) if with_bias else None
+    ref = attn_ref(qd, kd, vd, mask, bd, 0.125)
+    ref.backward(go.double())
+    o = torch.empty(B, Nq, I, device=DEV, dtype=dtype)
+    k.attn_fwd(B, h, Nq, Nk, q.data_ptr(), I, kk.data_ptr(), I, v.data_ptr(), I, mask, bias, o, I, 0.125)
+    tol = 2e-6 if dtype == torch.float32 else 8e-3
+    assert normwise(o, ref) < tol
+    if B > 1:
+        assert normwise(o[B - 1].float(), v[B - 1].float().mean(0, keepdim=True).expand(Nq, I)) < (1e-5 if dtype == torch.float32 else 1e-2)
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(kk), torch.empty_like(v)
+    dbias = torch.empty(B, h, Nq, Nk, device=DEV) if with_bias else None
+    k.attn_bwd(B, h, Nq, Nk, q.data_ptr(), I, kk.data_ptr(), I, v.data_ptr(), I, mask, bias, o, I, go, I,
+               dq.data_ptr(), I, dk.data_ptr(), I, dv.data_ptr(), I, dbias, 0.125)
+    tolb = 1e-5 if dtype == torch.float32 else 2e-2
+    assert normwise(dq, qd.grad) < tolb
+    assert normwise(dk, kd.grad) < tolb
+    assert normwise(dv, vd.grad) < tolb
+    if with_bias:
+        assert normwise(dbias, bd.grad) < tolb
+
+
+def test_attention_dropout_statistics_and_grad_consistency():
+    k = K()
+    B, h, N = 4, 2, 64
+    I = 64 * h
+    q, kk = torch.zeros(B, N, I, device=DEV), torch.zeros(B, N, I, device=DEV)   # uniform attention 1/N
+    v = torch.ones(B, N, I, device=DEV)
+    st = torch.tensor([42, 3], dtype=torch.int64, device=DEV)
+    d = k.Drop(st, salt=11, p=0.1)
+    o = torch.empty(B, N, I, device=DEV)
+    k.attn_fwd(B, h, N, N, q.data_ptr(), I, kk.data_ptr(), I, v.data_ptr(), I, None, None, o, I, 0.125, drop=d)
+    # each output = (#kept / N) / 0.9 ; mean over many rows ~ 1
+    assert abs(float(o.mean()) - 1.0) < 0.01
+    assert float(o.std()) > 0.0
+    o2 = torch.empty_like(o)
+    k.attn_fwd(B, h, N, N, q.data_ptr(), I, kk.data_ptr(), I, v.data_ptr(), I, None, None, o2, I, 0.125, drop=d)
+    assert torch.equal(o, o2)             # same (state, salt) -> same mask
+    st2 = torch.tensor([42, 4], dtype=torch.int64, device=DEV)
+    k.attn_fwd(B, h, N, N, q.data_ptr(), I, kk.data_ptr(), I, v.data_ptr(), I, None, None, o2, I, 0.125,
+               drop=k.Drop(st2, salt=11, p=0.1))
+    assert not torch.equal(o, o2)         # next step -> fresh mask
+
+
+# ------------------------------------------------------------------------------------------ RSA geometry bias
+@pytest.mark.parametrize('mode', ['dense', 'geometry'])
+@pytest.mark.parametrize('B,N,h', [(2, 7, 2), (3, 100, 8), (1, 37, 4)])
+def test_relbias_fwd_bwd(mode, B, N, h):
+    k = K()
+    R = 64
+    g4 = rnd(B, N, N, 4, seed=1)
+    g4[0, N // 2:] = 0                    # zero-padded pairs, as the loader produces
+    Wy, by = 0.5 * rnd(R, 4, seed=2), 0.1 * rnd(R, seed=3)
+    Wr, br = 0.2 * rnd(h, R, seed=4), 0.1 * rnd(h, seed=5)
+    go = rnd(B, h, N, N, seed=6)
+    g4d, Wyd, byd, Wrd, brd = (t.double().requires_grad_(True) for t in (g4, Wy, by, Wr, br))
+    e = torch.relu(g4d @ Wyd.t() + byd)
+    if mode == 'dense':
+        e = e.detach().requires_grad_(True)
+    r = torch.relu(e @ Wrd.t() + brd).permute(0, 3, 1, 2)
+    ref = torch.log(torch.clamp(r, min=1e-6))
+    ref.backward(go.double())
+    bias = torch.empty(B, h, N, N, device=DEV)
+    dWr, dbr = torch.zeros_like(Wr), torch.zeros_like(br)
+    if mode == 'dense':
+        rel = e.detach().float().contiguous()
+        k.relbias_fwd(B, N, h, R, rel, None, None, None, Wr, br, bias)
+        drel = torch.empty_like(rel)
+        k.relbias_bwd(B, N, h, R, rel, None, None, None, Wr, br, go, drel, None, None, dWr, dbr)
+        assert normwise(drel, e.grad) < 1e-5
+    else:
+        k.relbias_fwd(B, N, h, R, None, g4, Wy, by, Wr, br, bias)
+        dWy, dby = torch.zeros_like(Wy), torch.zeros_like(by)
+        k.relbias_bwd(B, N, h, R, None, g4, Wy, by, Wr, br, go, None, dWy, dby, dWr, dbr)
+        assert normwise(dWy, Wyd.grad) < 2e-5
+        assert normwise(dby, byd.grad) < 2e-5
+    # entries sitting exactly on the relu / clamp kink can flip between fp32 and fp64: compare away from it
+    safe = (r.detach() > 1e-4) | (r.detach() == 0)
+    assert normwise(bias[safe], ref[safe]) < 1e-5
+    assert normwise(dWr, Wrd.grad) < 2e-5
+    assert normwise(dbr, brd.grad) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------ mixed-op, helpers
+@pytest.mark.parametrize('Kc', [2, 4])
+def test_mixed_accum_and_alpha_dot(Kc):
+    k = K()
+    n = 64 * 100 * 256
+    outs = [rnd(n, seed=10 + i) for i in range(Kc)]
+    gate = torch.zeros(Kc, device=DEV)
+    gate[1] = 1.0
+    out = torch.empty(n, device=DEV)
+    k.mixed_accum(outs, gate, out)
+    assert torch.equal(out, outs[1])          # one-hot gate: exact
+    gate2 = rnd(Kc, seed=3)
+    k.mixed_accum(outs, gate2, out)
+    ref = sum(g.double() * o.double() for g, o in zip(gate2, outs))
+    assert normwise(out, ref) < 1e-6
+    dout = rnd(n, seed=4)
+    gg = torch.empty(Kc, device=DEV)
+    d_outs = [torch.empty(n, device=DEV), None] + [None] * (Kc - 2)
+    k.mixed_alpha_dot(outs, gate2, dout, gg, d_outs)
+    ref_gg = torch.stack([(o.double() * dout.double()).sum() for o in outs])
+    assert normwise(gg, ref_gg) < 1e-5
+    assert normwise(d_outs[0], gate2[0].double() * dout.double()) < 1e-6
+
+
+def test_cast_and_colsum():
+    k = K()
+    x = rnd(1000, 513, seed=1)
+    x16 = k.cast_bf16(x)
+    assert torch.equal(x16, x.bfloat16())
+    out = torch.empty(513, device=DEV)
+    k.colsum(x, 1000, 513, 513, out)
+    assert normwise(out, x.double().sum(0)) < 1e-5
+    k.colsum(x16, 1000, 513, 513, out)
+    assert normwise(out, x16.double().sum(0)) < 1e-5
+
+
+def test_bad_arguments_raise():
+    from mmnas_b200._lib import MMnasLibraryError
+    k = K()
+    q = rnd(1, 8, 32)
+    o = torch.empty_like(q)
+    with pytest.raises(MMnasLibraryError):     # head dim 32 is not implemented: loud, no fallback
+        k.attn_fwd(1, 1, 8, 8, q.data_ptr(), 32, q.data_ptr(), 32, q.data_ptr(), 32, None, None, o, 32, 0.1, head_dim=32)
+    with pytest.raises(MMnasLibraryError):
+        k.gemm_bf16(8, 30, 8, q.bfloat16(), 8, 0, q.bfloat16(), 8, 0, o, 30)   # N % 32 != 0
