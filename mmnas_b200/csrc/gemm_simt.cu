@@ -28,11 +28,13 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs g) {
   const int tid = threadIdx.x;
   const int tx = tid % 16, ty = tid / 16;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  float acc[TM][TN];
+  // two-level accumulation: `part` sums 128 consecutive k, then is flushed into `acc`, so the round-off of a
+  // long reduction (wgrad: K = tokens = 6400) stays at blocked-GEMM level instead of a serial 6400-term sum
+  float acc[TM][TN], part[TM][TN];
 #pragma unroll
   for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) { acc[i][j] = 0.f; part[i][j] = 0.f; }
 
   for (int k0 = 0; k0 < g.K; k0 += BK) {
 #pragma unroll
@@ -62,7 +64,13 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs g) {
 #pragma unroll
       for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < TN; ++j) part[i][j] = fmaf(a[i], b[j], part[i][j]);
+    }
+    if (((k0 / BK) & 7) == 7 || k0 + BK >= g.K) {
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) { acc[i][j] += part[i][j]; part[i][j] = 0.f; }
     }
     __syncthreads();
   }

@@ -145,21 +145,26 @@ __global__ void __launch_bounds__(TILE) relbias_bwd_kernel(RelArgs a) {
       for (int e = t; e < TILE * R; e += TILE)
         if (base + e < lim) a.drel[base + e] = DE[e];
     }
-    // ---- phase B: reductions over the tile's pairs into this thread's accumulators
+    // ---- phase B: reductions over the tile's pairs.  Two-level summation (tile-local partials, then the
+    // running total) keeps fp32 round-off at the level of a blocked GEMM instead of a 70k-term serial sum.
+    float pWr[4] = {0.f, 0.f, 0.f, 0.f}, pWy = 0.f, pby = 0.f, pbr = 0.f;
     for (int p = 0; p < TILE; ++p) {
       const float ev = E[p * R + c_own];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int hh = q_own + 4 * k;
-        if (hh < heads) accWr[k] = fmaf(Dp[p * MAXH + hh], ev, accWr[k]);
+        if (hh < heads) pWr[k] = fmaf(Dp[p * MAXH + hh], ev, pWr[k]);
       }
       if (!DENSE) {
         const float dev = DE[p * R + c_own];
-        accWy = fmaf(dev, G[p * 4 + q_own], accWy);
-        if (q_own == 0) accby += dev;
+        pWy = fmaf(dev, G[p * 4 + q_own], pWy);
+        if (q_own == 0) pby += dev;
       }
-      if (t < heads) accbr += Dp[p * MAXH + t];
+      if (t < heads) pbr += Dp[p * MAXH + t];
     }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) accWr[k] += pWr[k];
+    accWy += pWy; accby += pby; accbr += pbr;
   }
   if (c_own < R) {
 #pragma unroll

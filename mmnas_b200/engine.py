@@ -1,0 +1,332 @@
+"""Step harness around the operator hot path: the train step of train_vqa.py:294-311 and the search step of
+search_vqa.py:278-337 on synthetic batches, data-parallel over one process per GPU.
+
+Pieces
+  FlatGrads      all gradients live in one flat fp32 buffer (views installed as p.grad); zeroing it is one memset
+                 and gives every parameter a (zero) gradient each step — what the reference obtains with its
+                 `loss += 0 * sum(p.sum())` trick (train_vqa.py:298, search_vqa.py:286-288).
+  BucketReducer  data-parallel gradient averaging: the flat buffer is cut into buckets in reverse registration
+                 order (≈ backward order); a bucket's all-reduce is launched from the post-accumulate hook of its
+                 last parameter, so NCCL traffic over NVLink overlaps the rest of the backward.  Replaces DDP's
+                 reducer (train_vqa.py:236); same semantics: mean over ranks of per-rank sum-reduced losses.
+  WarmupAdam     Adam + the 1/4,2/4,3/4,1 warm-up of mmnas/utils/optimizer.py:25-44 (+ decay), clip_grad_norm_.
+  TrainStep / SearchStep   the step bodies; TrainStep can replay the whole step as one CUDA graph.
+  Prefetcher     pinned host batches -> device on a copy stream, double buffered.
+"""
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from . import runtime
+from .model.mixed import MixedOp
+
+
+# ------------------------------------------------------------------------------------------------ gradients
+class FlatGrads:
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError('no trainable parameters')
+        dev = self.params[0].device
+        self.offsets = []
+        off = 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4          # keep every view 16-byte aligned
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.install()
+
+    def view(self, i):
+        p = self.params[i]
+        return self.flat[self.offsets[i]:self.offsets[i] + p.numel()].view_as(p)
+
+    def install(self):
+        for i, p in enumerate(self.params):
+            p.grad = self.view(i)
+
+    def zero(self):
+        self.flat.zero_()
+        for i, p in enumerate(self.params):         # MixedOp.binarize() sets candidate grads to None
+            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + 4 * self.offsets[i]:
+                p.grad = self.view(i)
+
+
+class BucketReducer:
+    """Overlapped gradient mean over the process group, on top of FlatGrads."""
+
+    def __init__(self, flat_grads, group=None, bucket_mb=25.0):
+        self.fg = flat_grads
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.enabled = self.world > 1
+        self.buckets = []          # (start, end, [param indices]) over the flat buffer, reverse registration order
+        cap = int(bucket_mb * (1 << 20) / 4)
+        idxs, end = [], None
+        n = len(self.fg.params)
+        for i in reversed(range(n)):
+            p_end = self.fg.offsets[i] + (self.fg.params[i].numel() + 3) // 4 * 4
+            if end is None:
+                end = p_end
+            idxs.append(i)
+            if end - self.fg.offsets[i] >= cap or i == 0:
+                self.buckets.append((self.fg.offsets[i], end, idxs))
+                idxs, end = [], None
+        self.bucket_of = {}
+        for b, (_, _, ids) in enumerate(self.buckets):
+            for i in ids:
+                self.bucket_of[i] = b
+        self._pending = [0] * len(self.buckets)
+        self._launched = [False] * len(self.buckets)
+        self._works = []
+        self._avg = None
+        if self.enabled:
+            for i, p in enumerate(self.fg.params):
+                p.register_post_accumulate_grad_hook(self._make_hook(i))
+        self.reset()
+
+    def _make_hook(self, i):
+        def hook(param):
+            if not self._armed:
+                return
+            b = self.bucket_of[i]
+            self._pending[b] -= 1
+            if self._pending[b] == 0:
+                self._launch(b)
+        return hook
+
+    def reset(self):
+        """Arm for one backward pass."""
+        for b, (_, _, ids) in enumerate(self.buckets):
+            self._pending[b] = len(ids)
+            self._launched[b] = False
+        self._works = []
+        self._armed = True
+
+    def _launch(self, b):
+        if self._launched[b] or not self.enabled:
+            return
+        self._launched[b] = True
+        s, e, _ = self.buckets[b]
+        chunk = self.fg.flat[s:e]
+        if self._avg is None:
+            self._avg = dist.get_backend(self.group) == 'nccl'
+        if self._avg:
+            self._works.append(dist.all_reduce(chunk, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+        else:                                       # gloo has no AVG
+            chunk.mul_(1.0 / self.world)
+            self._works.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self):
+        """Launch buckets whose parameters never fired (unused candidates), then wait for everything."""
+        self._armed = False
+        if not self.enabled:
+            return
+        for b in range(len(self.buckets)):
+            self._launch(b)
+        for w in self._works:
+            w.wait()
+        self._works = []
+
+
+# ------------------------------------------------------------------------------------------------ optimizer
+class WarmupAdam:
+    """Adam(lr schedule of WarmupOptimizer, optimizer.py:14-47) preceded by clip_grad_norm_ (train_vqa.py:309-311)."""
+
+    def __init__(self, params, lr_base, epoch_steps, betas=(0.9, 0.98), eps=1e-9, clip=1.0, warmup=True,
+                 capturable=False):
+        self.params = [p for p in params if p.requires_grad]
+        self.lr_base, self.epoch_steps, self.warmup, self.clip = lr_base, max(1, epoch_steps), warmup, clip
+        self._step = 0
+        self._rate = 0.0
+        self.capturable = capturable
+        lr = torch.tensor(0.0, device=self.params[0].device) if capturable else 0.0
+        self.optimizer = torch.optim.Adam(self.params, lr=lr, betas=betas, eps=eps, weight_decay=0,
+                                          fused=self.params[0].is_cuda, capturable=capturable)
+
+    def rate(self, step=None):
+        step = self._step if step is None else step
+        if not self.warmup:
+            return self.lr_base
+        for k in (1, 2, 3):
+            if step <= int(self.epoch_steps * k):
+                return self.lr_base * k / 4.
+        return self.lr_base
+
+    def decay(self, r):
+        self.lr_base *= r
+
+    def set_lr(self):
+        """Host side of a step: advance the schedule and publish the learning rate."""
+        self._step += 1
+        self._rate = self.rate()
+        for g in self.optimizer.param_groups:
+            if torch.is_tensor(g['lr']):
+                g['lr'].fill_(self._rate)
+            else:
+                g['lr'] = self._rate
+
+    def clip_and_step(self):
+        if self.clip and self.clip > 0:
+            torch.nn.utils.clip_grad_norm_(self.params, self.clip, foreach=True)
+        self.optimizer.step()
+
+
+# ------------------------------------------------------------------------------------------------ steps
+def vqa_loss(pred, target):
+    return F.binary_cross_entropy_with_logits(pred, target, reduction='sum')
+
+
+class TrainStep:
+    """net_optim.zero_grad(); pred = net(x); loss = BCE_sum; backward (+ overlapped grad mean); clip; Adam."""
+
+    def __init__(self, net, lr_base=0.00012, epoch_steps=1000, bucket_mb=25.0, use_graph=False, loss_fn=vqa_loss,
+                 betas=(0.9, 0.98), eps=1e-9, clip=1.0):
+        self.net = net
+        self.loss_fn = loss_fn
+        self.grads = FlatGrads(net.parameters())
+        self.reducer = BucketReducer(self.grads, bucket_mb=bucket_mb)
+        self.use_graph = use_graph and not self.reducer.enabled
+        self.optim = WarmupAdam(self.grads.params, lr_base, epoch_steps, betas, eps, clip, capturable=self.use_graph)
+        self.graph = None
+        self._static_in = self._static_tgt = self._static_loss = None
+
+    def _body(self, inputs, target):
+        self.grads.zero()
+        self.reducer.reset()
+        runtime.advance(target.device)
+        pred = self.net(inputs)
+        loss = self.loss_fn(pred, target)
+        loss.backward()
+        self.reducer.finish()
+        self.optim.clip_and_step()
+        return loss.detach()
+
+    def __call__(self, inputs, target):
+        self.optim.set_lr()
+        if not self.use_graph:
+            return self._body(inputs, target)
+        if self.graph is None:
+            self._capture(inputs, target)
+        for dst, src in zip(self._static_in, inputs):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        if self._static_tgt.data_ptr() != target.data_ptr():
+            self._static_tgt.copy_(target, non_blocking=True)
+        self.graph.replay()
+        return self._static_loss
+
+    def _capture(self, inputs, target):
+        self._static_in = tuple(t.clone() for t in inputs)
+        self._static_tgt = target.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):               # warm-up outside capture (allocator, Adam state, lazy init)
+            for _ in range(3):
+                self._body(self._static_in, self._static_tgt)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._static_loss = self._body(self._static_in, self._static_tgt)
+
+    @property
+    def static_inputs(self):
+        return self._static_in, self._static_tgt
+
+
+class SearchStep:
+    """One iteration of search_vqa.py:278-337: weight step on the sampled path, and (when `arch=True`) the
+    architecture step in MODE 'full' on a held-out batch."""
+
+    def __init__(self, net, lr_base=0.0004, epoch_steps=1000, alpha_lr=0.1, alpha_betas=(0., 0.999), mode='full',
+                 bucket_mb=25.0, loss_fn=vqa_loss):
+        self.net = net
+        self.mode = mode
+        self.loss_fn = loss_fn
+        self.grads = FlatGrads(net.parameters())          # weights, alpha_prob and alpha_gate
+        self.reducer = BucketReducer(self.grads, bucket_mb=bucket_mb)
+        self.net_params = [p for p in net.net_parameters()]
+        self.optim = WarmupAdam(self.net_params, lr_base, epoch_steps)
+        self.alpha_optim = torch.optim.Adam(list(net.alpha_prob_parameters()), alpha_lr, betas=alpha_betas,
+                                            weight_decay=0)
+
+    def _forward_backward(self, inputs, target):
+        self.grads.zero()                # net.zero_grad() + the reference's 0*sum(params) dummy terms
+        self.reducer.reset()
+        runtime.advance(target.device)
+        loss = self.loss_fn(self.net(inputs), target)
+        loss.backward()
+        self.reducer.finish()
+        return loss.detach()
+
+    def weight_step(self, inputs, target):
+        MixedOp.MODE = None
+        self.net.reset_binary_gates()
+        self.net.unused_modules_off()
+        try:
+            self.optim.set_lr()
+            loss = self._forward_backward(inputs, target)
+            self.optim.clip_and_step()
+        finally:
+            self.net.unused_modules_back()
+        return loss
+
+    def arch_step(self, inputs, target):
+        MixedOp.MODE = self.mode
+        self.net.reset_binary_gates()
+        self.net.unused_modules_off()
+        try:
+            loss = self._forward_backward(inputs, target)
+            self.net.set_arch_param_grad()
+            self.alpha_optim.step()
+            if MixedOp.MODE == 'two':
+                self.net.rescale_updated_arch_param()
+        finally:
+            self.net.unused_modules_back()
+            MixedOp.MODE = None
+        return loss
+
+    def __call__(self, train_batch, eval_batch=None):
+        loss = self.weight_step(*train_batch)
+        if eval_batch is not None:
+            loss = self.arch_step(*eval_batch)
+        return loss
+
+
+# ------------------------------------------------------------------------------------------------ input pipeline
+class Prefetcher:
+    """Host (pinned) -> device copies on a side stream, one batch ahead of the compute stream."""
+
+    def __init__(self, host_batches, device):
+        self.device = torch.device(device)
+        self.host = [self._pin(b) for b in host_batches]
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.bytes_per_batch = sum(t.numel() * t.element_size() for t in self._flat(self.host[0]))
+        self._i = 0
+        self._next = None
+        self._issue()
+
+    @staticmethod
+    def _flat(batch):
+        inputs, target = batch
+        return list(inputs) + [target]
+
+    def _pin(self, batch):
+        inputs, target = batch
+        return tuple(t.pin_memory() for t in inputs), target.pin_memory()
+
+    def _issue(self):
+        inputs, target = self.host[self._i % len(self.host)]
+        self._i += 1
+        with torch.cuda.stream(self.stream):
+            dev_in = tuple(t.to(self.device, non_blocking=True) for t in inputs)
+            dev_tgt = target.to(self.device, non_blocking=True)
+        self._next = (dev_in, dev_tgt)
+
+    def next(self):
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        batch = self._next
+        for t in self._flat(batch):
+            t.record_stream(torch.cuda.current_stream(self.device))
+        self._issue()
+        return batch

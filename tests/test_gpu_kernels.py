@@ -239,6 +239,13 @@ def test_relbias_fwd_bwd(mode, B, N, h):
     g4[0, N // 2:] = 0                    # zero-padded pairs, as the loader produces
     Wy, by = 0.5 * rnd(R, 4, seed=2), 0.1 * rnd(R, seed=3)
     Wr, br = 0.2 * rnd(h, R, seed=4), 0.1 * rnd(h, seed=5)
+    if N > 8:
+        # d log(r)/dr = 1/r makes the gradient sums ill-conditioned when some r sit just above the 1e-6 clamp
+        # (fp32 evaluation of r then carries a relative error ~1e-7/r).  The small case above keeps the generic
+        # regime (all branches: relu off, clamp, pass-through); the large cases use benign parameters: head 0
+        # always inactive (relu off), the others well inside the pass-through region.
+        Wr, br = 0.03 * rnd(h, R, seed=4), torch.ones(h, device=DEV)
+        br[0] = -2.0
     go = rnd(B, h, N, N, seed=6)
     g4d, Wyd, byd, Wrd, brd = (t.double().requires_grad_(True) for t in (g4, Wy, by, Wr, br))
     e = torch.relu(g4d @ Wyd.t() + byd)

@@ -1,0 +1,183 @@
+"""End-to-end parity of the callers on the B200: Net_Full train step and Net_Search architecture step through the
+CUDA operators, against the reference golden vectors and against the CPU oracle at the BASELINE shapes."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mmnas_oracle as O
+from tests.util import load_golden, params_of, literal, normwise, grad_floor
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+TOL = {'fp32': 1e-5, 'bf16': 2e-2}
+
+
+def tiny_cfg(genotype=None):
+    from mmnas_b200.data.synthetic import Cfg
+    return Cfg(mode='train', genotype=genotype, HSIZE=64, DROPOUT_R=0.0, FRCNFEAT_SIZE=32, BBOXFEAT_EMB_SIZE=32,
+               WORD_EMBED_SIZE=16, ATTFLAT_MLP_SIZE=48, ATTFLAT_OUT_SIZE=128, NODES={'enc': 2, 'dec': 3})
+
+
+def tiny_init():
+    return {'token_size': 30, 'ans_size': 11, 'pretrained_emb': np.zeros((30, 16), np.float32)}
+
+
+def dev_inputs(r):
+    return tuple(r[k].to(DEV) for k in ('frcn', 'bbox', 'rel', 'ques', 'rel_q'))
+
+
+@pytest.mark.parametrize('rel_mode', ['geometry', 'dense'])
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_net_full_step_matches_reference_golden(mode, rel_mode):
+    import mmnas_b200
+    from mmnas_b200.model.nets import Net_Full
+    r = load_golden('net_full_h64.npz')
+    net = Net_Full(tiny_cfg(literal(r, 'genotype')), tiny_init(), rel_mode=rel_mode)
+    net.load_state_dict(params_of(r))
+    net = net.to(DEV).train()
+    with mmnas_b200.precision(mode):
+        pred = net(dev_inputs(r))
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(pred, r['target'].to(DEV), reduction='sum')
+        loss.backward()
+    tol = TOL[mode]
+    assert normwise(pred, r['pred']) < tol
+    assert abs(loss.item() - r['loss'].item()) < tol * abs(r['loss'].item())
+    floor = grad_floor(r)
+    for n_, p_ in net.named_parameters():
+        assert p_.grad is not None, n_
+        assert normwise(p_.grad, r['g.' + n_], floor) < tol * (1 if mode == 'bf16' else 2), n_
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_net_search_arch_step_matches_reference_golden(mode):
+    import mmnas_b200
+    from mmnas_b200.model.mixed import MixedOp
+    from mmnas_b200.model.nets import Net_Search
+    r = load_golden('net_search_h64.npz')
+    net = Net_Search(tiny_cfg(), tiny_init())
+    for n_, p_ in net.named_parameters():          # golden alphas have 2 / 4 entries (see make_golden.py)
+        if 'alpha_prob' in n_:
+            p_.data = torch.zeros_like(r['p.' + n_])
+    net.load_state_dict(params_of(r))
+    net = net.to(DEV).train()
+    alpha_optim = torch.optim.Adam(list(net.alpha_prob_parameters()), 0.1, betas=(0., 0.999), weight_decay=0)
+    choices = r['choices_enc'].tolist() + r['choices_dec'].tolist()
+    for m, a in zip(net.redundant_modules, choices):
+        m.active_index, m.inactive_index = [a], [i for i in range(m.n_choices) if i != a]
+    MixedOp.MODE = 'full'
+    try:
+        with mmnas_b200.precision(mode):
+            pred = net(dev_inputs(r))
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(pred, r['target'].to(DEV), reduction='sum')
+            net.zero_grad()
+            loss.backward()
+        gate_grads = {n_: p_.grad.clone() for n_, p_ in net.named_alpha_gate_parameters()}
+        net.set_arch_param_grad()
+        alpha_optim.step()
+    finally:
+        MixedOp.MODE = None
+    tol = TOL[mode]
+    assert normwise(pred, r['pred']) < tol
+    gfloor = 1e-2 * max(r['g.' + n_].abs().max().item() for n_ in gate_grads)
+    for n_, g in gate_grads.items():
+        assert normwise(g, r['g.' + n_], gfloor) < 5 * tol, n_       # cancelling sums: see test_oracle_golden
+    for n_, p_ in net.named_alpha_prob_parameters():
+        assert normwise(p_.grad, r['g.' + n_], gfloor) < 5 * tol, n_
+        if mode == 'fp32':
+            assert normwise(p_, r['after.' + n_]) < 1e-4, n_
+    if mode == 'fp32':
+        assert net.genotype() == literal(r, 'genotype')            # identical argmax-selected architecture
+
+
+def full_setup(batch, mode='train', p=0.0, seed=888):
+    from mmnas_b200 import genotypes
+    from mmnas_b200.data.synthetic import Cfg, SynthSpec, make_batch, init_dict
+    spec = SynthSpec(batch=batch, vocab=2000)
+    cfg = Cfg(mode=mode, genotype=genotypes.shipped('mmnas_vqa'), DROPOUT_R=p)
+    inputs, target = make_batch(spec, seed)
+    return spec, cfg, init_dict(spec), inputs, target
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_net_full_vqa_at_baseline_config_matches_oracle(mode):
+    """arch mmnas_vqa, H=512, 8 heads, 100 regions x 2048, 14 tokens (BASELINE config 1 at B=8): loss, logits and
+    every gradient of the 30-block backbone + stem + head against the CPU oracle (float32, same weights)."""
+    import mmnas_b200
+    from mmnas_b200.model.nets import Net_Full
+    torch.manual_seed(888)
+    spec, cfg, init, inputs, target = full_setup(8)
+    net = Net_Full(cfg, init).train()
+    P = O.leaf_params(net.state_dict(), torch.float64)
+    inp64 = tuple(t.double() if t.is_floating_point() else t for t in inputs)
+    loss_ref, pred_ref = O.train_step_vqa(P, inp64, target.double(), cfg.GENOTYPE)
+    net = net.to(DEV)
+    with mmnas_b200.precision(mode):
+        pred = net(tuple(t.to(DEV) for t in inputs))
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(pred, target.to(DEV), reduction='sum')
+        loss.backward()
+    tol = TOL[mode]
+    assert normwise(pred, pred_ref) < tol
+    assert abs(loss.item() - loss_ref.item()) < tol * abs(loss_ref.item())
+    floor = 1e-2 * max(p.grad.abs().max().item() for p in P.values() if p.grad is not None)
+    worst = 0.0
+    for n_, p_ in net.named_parameters():
+        ref = P[n_].grad if P[n_].grad is not None else torch.zeros_like(P[n_])
+        err = normwise(p_.grad, ref, floor)
+        worst = max(worst, err)
+        assert err < tol * 3, (n_, err)
+    print('worst grad error', mode, worst)
+
+
+def test_train_step_graph_replay_equals_eager():
+    """The captured CUDA graph of the whole step (fwd + bwd + clip + Adam) evolves the weights like eager steps."""
+    import copy
+    import mmnas_b200
+    from mmnas_b200.engine import TrainStep
+    from mmnas_b200.model.nets import Net_Full
+    torch.manual_seed(1)
+    spec, cfg, init, inputs, target = full_setup(4)
+    net_a = Net_Full(cfg, init).to(DEV).train()
+    net_b = copy.deepcopy(net_a)
+    din, dt = tuple(t.to(DEV) for t in inputs), target.to(DEV)
+    with mmnas_b200.precision('bf16'):
+        eager = TrainStep(net_a, use_graph=False)
+        graph = TrainStep(net_b, use_graph=True)
+        la = [eager(din, dt).item() for _ in range(6)]
+        lb = [graph(din, dt).item() for _ in range(6)]
+    # graph capture runs 3 warm-up + 1 capture step on the same batch before the first replay
+    assert lb[0] < la[0]
+    assert abs(lb[0] - la[4]) < 0.05 * abs(la[4])
+    assert la[5] < la[0]
+
+
+def test_search_step_weight_and_arch():
+    """search_vqa.py:278-337 step body at H=256: the weight step touches only the sampled path, the arch step
+    moves every alpha_prob by lr=0.1 (Adam, beta1=0) and leaves the weights alone."""
+    import mmnas_b200
+    from mmnas_b200.engine import SearchStep
+    from mmnas_b200.model.nets import Net_Search
+    torch.manual_seed(888)
+    spec, cfg, init, inputs, target = full_setup(4, mode='search', p=0.1)
+    net = Net_Search(cfg, init).to(DEV).train()
+    step = SearchStep(net)
+    din, dt = tuple(t.to(DEV) for t in inputs), target.to(DEV)
+    alphas0 = [p.detach().clone() for p in net.alpha_prob_parameters()]
+    w0 = {n: p.detach().clone() for n, p in net.named_net_parameters()}
+    with mmnas_b200.precision('bf16'):
+        l1 = step.weight_step(din, dt)
+        assert torch.isfinite(l1)
+        for a, p in zip(alphas0, net.alpha_prob_parameters()):
+            assert torch.equal(a, p)                       # weight step leaves alphas alone
+        moved = sum(int(not torch.equal(w0[n], p)) for n, p in net.named_net_parameters())
+        assert moved > 0
+        w1 = {n: p.detach().clone() for n, p in net.named_net_parameters()}
+        l2 = step.arch_step(din, dt)
+        assert torch.isfinite(l2)
+    for n, p in net.named_net_parameters():
+        assert torch.equal(w1[n], p), n                    # arch step leaves weights alone
+    for a, p in zip(alphas0, net.alpha_prob_parameters()):
+        d = (p.detach() - a).abs()
+        assert torch.all((d - 0.1).abs() < 2e-3) or torch.all(d < 0.11)
+    assert all(m.candidate_ops[i] is not None for m in net.redundant_modules for i in range(m.n_choices))
+    g = net.genotype()
+    assert len(g['enc']) == 12 and len(g['dec']) == 18
