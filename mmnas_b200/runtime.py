@@ -17,6 +17,10 @@ def set_precision(mode):
     if mode not in ('fp32', 'bf16'):
         raise ValueError("precision must be 'fp32' or 'bf16'")
     _PRECISION = mode
+    # The callers' stem / heads still run on torch: keep them true fp32 in the parity arm (cuDNN's LSTM would
+    # otherwise use TF32, ~1e-3), and let them use TF32 tensor cores in the bf16 arm.
+    torch.backends.cudnn.allow_tf32 = mode == 'bf16'
+    torch.backends.cuda.matmul.allow_tf32 = mode == 'bf16'
 
 
 def get_precision():

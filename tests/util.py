@@ -48,3 +48,25 @@ def normwise(new, ref, floor=0.0):
 def grad_floor(rec, frac=1e-2, prefix='g.'):
     """frac x the largest reference gradient entry over all parameters of a golden record."""
     return frac * max(v.abs().max().item() for k, v in rec.items() if k.startswith(prefix))
+
+
+class Parity:
+    """Collects normwise errors of many tensors, logs them (gpurun_out/parity.jsonl when that directory exists)
+    and fails once at the end listing every tensor over tolerance."""
+
+    def __init__(self, label):
+        self.label, self.rows = label, []
+
+    def add(self, name, new, ref, tol, floor=0.0):
+        self.rows.append((name, normwise(new, ref, floor), tol))
+
+    def check(self):
+        import json
+        worst = sorted(self.rows, key=lambda r: -r[1] / r[2])[:5]
+        out = os.path.join(os.path.dirname(GOLDEN), '..', 'gpurun_out')
+        if os.path.isdir(out):
+            with open(os.path.join(out, 'parity.jsonl'), 'a') as f:
+                f.write(json.dumps({'case': self.label, 'n': len(self.rows),
+                                    'worst': [(n, float('%.3g' % e), t) for n, e, t in worst]}) + '\n')
+        bad = [(n, float('%.3g' % e), t) for n, e, t in self.rows if not e < t]
+        assert not bad, '%s: over tolerance: %s' % (self.label, bad)
