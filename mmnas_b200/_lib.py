@@ -64,11 +64,38 @@ def load():
     return lib
 
 
+LAUNCHES = 0          # number of C-ABI kernel entry points invoked (bench.py's `gpu_launches` claim)
+_profile = None       # when a list: (name, args, start_event, end_event) per call — bench.py's live kernel timing
+
+
 def call(name, *args):
+    global LAUNCHES
     lib = load()
-    rc = getattr(lib, name)(*args)
+    LAUNCHES += 1
+    if _profile is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        _profile.append((name, args, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise MMnasLibraryError('%s failed (%d): %s' % (name, rc, lib.mmnas_last_error().decode()))
+
+
+def profile_begin():
+    """Start recording a CUDA-event pair around every C-ABI call on the current stream."""
+    global _profile
+    _profile = []
+
+
+def profile_end():
+    """Stop recording; returns [(entry point, args, milliseconds)] after synchronising."""
+    global _profile
+    rec, _profile = _profile, None
+    torch.cuda.synchronize()
+    return [(n, a, e0.elapsed_time(e1)) for n, a, e0, e1 in rec]
 
 
 def ptr(t):

