@@ -177,6 +177,8 @@ def kernel_table(records):
             flops = 2.0 * M * N * K_
             byts = 2.0 * (M * K_ + N * K_) + (2.0 if a[11] else 4.0) * M * N
             key = 'gemm_bf16[%s%s]' % ('mn' if a[5] else 'k', 'mn' if a[8] else 'k')
+            if os.environ.get('MMNAS_PROFILE_SHAPES'):
+                key += ' %dx%dx%d%s' % (M, N, K_, ' sk%d' % a[18] if a[18] > 1 else '')
         elif name == 'mmnas_gemm_f32':
             flops = 2.0 * a[0] * a[1] * a[2]
             byts = 4.0 * (a[0] * a[2] + a[1] * a[2] + a[0] * a[1])

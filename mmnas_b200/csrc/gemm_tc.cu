@@ -1,26 +1,40 @@
 // bf16 tensor-core GEMM for sm_100a: TMA (cp.async.bulk.tensor) -> 128B-swizzled shared memory ->
-// tcgen05.mma (cta_group::1, 128xBNx16, kind::f16, fp32 accumulate in TMEM) -> tcgen05.ld epilogue.
+// tcgen05.mma (cta_group::1, 128 x BN x 16, kind::f16, fp32 accumulators in TMEM) -> tcgen05.ld epilogue.
 // Serves every dense contraction of the MMnas blocks in bf16 mode:
 //   forward   Y = X W^T        A K-major  [M,K],  B K-major  [N,K]            (nn.Linear, modules.py:18,38,172-175)
 //   dgrad     dX = dY W        A K-major  [M,N'], B MN-major (W itself, [N',K'])
-//   wgrad     dW = dY^T X      A MN-major (dY, [M,N']), B MN-major (X, [M,K'])  + split-K over M
-// so no transposed copies of activations or weights are ever materialised.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer (one elected
-// lane), warps 2..5 = epilogue (each owns the 32 TMEM lanes of its warp%4 quarter).
-// Fused epilogues: +bias, ReLU, dropout, ReLU-mask of a saved activation (FFN backward),
-// accumulate into fp32 C (residual-gradient add), bf16 or fp32 store, split-K red.add.
+//   wgrad     dW = dY^T X      A MN-major (dY, [M,N']), B MN-major (X, [M,K'])  + split-K over tokens
+// so no transposed copy of an activation or a weight is ever materialised.
+//
+// v2: persistent, warp-specialised, software-pipelined over tiles.
+//   grid = min(#work units, #SMs); a work unit = (split, m-tile, n-tile), n fastest so concurrently running CTAs
+//   share the A tile in L2.  Warp 0 = TMA producer (STAGES-deep smem ring), warp 1 = MMA issuer (one elected lane)
+//   + TMEM allocator, warps 2..5 = epilogue.  TMEM holds TWO accumulator buffers, so the epilogue of unit i
+//   overlaps the main loop of unit i+1 (v1 paid prologue + fill + epilogue serially per tile and ran at 10 %).
+//   Epilogue: tcgen05.ld (each warp owns the 32 TMEM lanes of its warp%4 quarter) -> padded smem staging ->
+//   re-read row-contiguous, so every global access is a full 64/128-byte row segment; all fused epilogue math
+//   (+bias, ReLU, dropout with one hash per 4 elements, ReLU-mask of a saved activation, fp32 accumulate,
+//   bf16/fp32 store, split-K red.add.v4) happens in that coalesced layout.
+//   BN = 256 (single 128x256x16 UMMA, half the operand traffic per FLOP) when it does not cost a wave.
 #include <cuda.h>
 #include "common.cuh"
 #include "../../include/mmnas_b200.h"
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
-constexpr int A_TILE_BYTES = BM * BK * 2, B_TILE_BYTES = BN * BK * 2;
-constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int BM = 128, BK = 64;
+constexpr int A_TILE_BYTES = BM * BK * 2;
 constexpr int NUM_THREADS = 192;
-constexpr uint32_t TMEM_COLS = BN;
+constexpr int STG_PITCH = 36;                         // floats per staged row (32 + 4 pad: 16B aligned, conflict free)
+constexpr int STG_BYTES = 4 * 32 * STG_PITCH * 4;     // 4 epilogue warps x 32 rows
+
+template <int BN> struct Cfg {
+  static constexpr int STAGES = BN == 128 ? 5 : 4;
+  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;       // two accumulator buffers
+};
 
 struct TcEpilogue {
   int M, N, K;
@@ -31,6 +45,7 @@ struct TcEpilogue {
   const __nv_bfloat16* aux; long ld_aux; float aux_scale;   // C = aux > 0 ? v * aux_scale : 0
   int use_drop; DropCfg drop;
   int split_k;                       // > 1: fp32 red.add into C
+  int tiles_m, tiles_n, kb_total, kb_per;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -40,6 +55,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
@@ -101,39 +119,84 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
-template <bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(NUM_THREADS)
+// epilogue math on 4 consecutive columns of one row, then the store — all accesses row-contiguous
+__device__ __forceinline__ void epilogue_store4(const TcEpilogue& ep, float4 v, int row, int col, bool add_bias, uint64_t key) {
+  if (add_bias) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+  }
+  if (ep.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+  if (ep.use_drop) {      // same stream as drop_mult(): one 64-bit hash per group of 4 elements
+    const uint64_t idx = (uint64_t)row * ep.N + col;
+    const uint64_t r = mmnas_mix64(key ^ ((idx >> 2) * 0x9E3779B97F4A7C15ull));
+    v.x *= ((unsigned)(r) & 0xFFFFu) < ep.drop.thresh ? 0.f : ep.drop.scale;
+    v.y *= ((unsigned)(r >> 16) & 0xFFFFu) < ep.drop.thresh ? 0.f : ep.drop.scale;
+    v.z *= ((unsigned)(r >> 32) & 0xFFFFu) < ep.drop.thresh ? 0.f : ep.drop.scale;
+    v.w *= ((unsigned)(r >> 48) & 0xFFFFu) < ep.drop.thresh ? 0.f : ep.drop.scale;
+  }
+  if (ep.aux) {
+    const uint2 pk = __ldg(reinterpret_cast<const uint2*>(ep.aux + (long)row * ep.ld_aux + col));
+    const __nv_bfloat162 a01 = *reinterpret_cast<const __nv_bfloat162*>(&pk.x);
+    const __nv_bfloat162 a23 = *reinterpret_cast<const __nv_bfloat162*>(&pk.y);
+    v.x = __low2float(a01) > 0.f ? v.x * ep.aux_scale : 0.f;
+    v.y = __high2float(a01) > 0.f ? v.y * ep.aux_scale : 0.f;
+    v.z = __low2float(a23) > 0.f ? v.z * ep.aux_scale : 0.f;
+    v.w = __high2float(a23) > 0.f ? v.w * ep.aux_scale : 0.f;
+  }
+  if (ep.out_bf16) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(ep.C) + (long)row * ep.ldc + col) = pk;
+  } else {
+    float* cp = reinterpret_cast<float*>(ep.C) + (long)row * ep.ldc + col;
+    if (ep.split_k > 1) {
+      red_add_v4(cp, v);
+    } else {
+      if (ep.accumulate) {
+        const float4 old = *reinterpret_cast<const float4*>(cp);
+        v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+      }
+      *reinterpret_cast<float4*>(cp) = v;
+    }
+  }
+}
+
+template <bool A_MN, bool B_MN, int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, TcEpilogue ep) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  // bars[0..S) full, bars[S..2S) empty, bars[2S] tmem_full; then the TMEM base address word
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  float* staging = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES + STG_BYTES);
+  // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty; then the TMEM base word
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
-  // split-K: this CTA reduces k-blocks [kb_begin, kb_end)
-  const int kb_total = (ep.K + BK - 1) / BK;
-  const int kb_per = (kb_total + ep.split_k - 1) / ep.split_k;
-  const int kb_begin = blockIdx.z * kb_per;
-  const int kb_end = min(kb_total, kb_begin + kb_per);
-  const int num_kb = kb_end - kb_begin;
+  const int units = ep.tiles_m * ep.tiles_n * ep.split_k;
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -141,16 +204,29 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  if (num_kb > 0) {
-    if (warp == 0 && lane == 0) {
-      // ===== TMA producer =====
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t phase = (i / STAGES) & 1;
-        mbar_wait(empty_bar(s), phase ^ 1);
-        mbar_expect_tx(full_bar(s), STAGE_BYTES);
-        const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_TILE_BYTES;
-        const int k0 = (kb_begin + i) * BK;
+  // unit -> (split z, m-tile, n-tile), n fastest
+  auto decode = [&](int u, int& z, int& m0, int& n0, int& kb0, int& nkb) {
+    const int tn = u % ep.tiles_n;
+    const int rest = u / ep.tiles_n;
+    const int tm = rest % ep.tiles_m;
+    z = rest / ep.tiles_m;
+    m0 = tm * BM; n0 = tn * BN;
+    kb0 = z * ep.kb_per;
+    nkb = min(ep.kb_total, kb0 + ep.kb_per) - kb0;
+  };
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer =====
+    uint32_t it = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      int z, m0, n0, kb0, nkb;
+      decode(u, z, m0, n0, kb0, nkb);
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(empty_bar(s), ((it / STAGES) & 1) ^ 1);
+        mbar_expect_tx(full_bar(s), C::STAGE_BYTES);
+        const uint32_t sa = smem_base + s * C::STAGE_BYTES, sb = sa + A_TILE_BYTES;
+        const int k0 = (kb0 + i) * BK;
         if (!A_MN) {
           tma_load_2d(sa, &tmap_a, full_bar(s), k0, m0);
         } else {
@@ -164,107 +240,77 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * (BK * 128), &tmap_b, full_bar(s), n0 + 64 * c, k0);
         }
       }
-    } else if (warp == 1 && lane == 0) {
-      // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc(A_MN, B_MN, BM, BN);
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t phase = (i / STAGES) & 1;
-        mbar_wait(full_bar(s), phase);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc(A_MN, B_MN, BM, BN);
+    uint32_t it = 0, j = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++j) {
+      int z, m0, n0, kb0, nkb;
+      decode(u, z, m0, n0, kb0, nkb);
+      const uint32_t buf = j & 1;
+      mbar_wait(tempty_bar(buf), ((j >> 1) & 1) ^ 1);          // epilogue has drained this accumulator
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tmem_d = tmem_base + buf * BN;
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(full_bar(s), (it / STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_TILE_BYTES;
+        const uint32_t sa = smem_base + s * C::STAGE_BYTES, sb = sa + A_TILE_BYTES;
 #pragma unroll
         for (int kk = 0; kk < BK / 16; ++kk) {
           // K-major: 16 k-elements = 32 B inside the 128 B swizzle row; SBO = 8 rows x 128 B.
           // MN-major: 16 k-rows x 128 B = 2048 B; SBO = 8 k-rows x 128 B, LBO = next 64-wide MN chunk.
           const uint64_t adesc = A_MN ? make_smem_desc(sa + kk * 2048, BK * 128, 1024) : make_smem_desc(sa + kk * 32, 16, 1024);
           const uint64_t bdesc = B_MN ? make_smem_desc(sb + kk * 2048, BK * 128, 1024) : make_smem_desc(sb + kk * 32, 16, 1024);
-          umma_bf16(tmem_base, adesc, bdesc, idesc, (i | kk) != 0 ? 1u : 0u);
+          umma_bf16(tmem_d, adesc, bdesc, idesc, (i | kk) != 0 ? 1u : 0u);
         }
         umma_commit(empty_bar(s));        // frees the smem stage when these MMAs retire
       }
-      umma_commit(tmem_full_bar);         // accumulator complete
+      umma_commit(tfull_bar(buf));        // accumulator of this unit complete
     }
-  }
-
-  if (warp >= 2) {
-    // ===== epilogue: TMEM -> registers -> global =====
+  } else if (warp >= 2) {
+    // ===== epilogue: TMEM -> registers -> smem staging -> coalesced global =====
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32)
-    const int row = m0 + quarter * 32 + lane;
-    if (num_kb > 0) {
-      mbar_wait(tmem_full_bar, 0);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    }
+    float* stg = staging + quarter * (32 * STG_PITCH);
     const uint64_t key = ep.use_drop ? drop_key(ep.drop) : 0;
-    const bool add_bias = ep.bias != nullptr && blockIdx.z == 0;
+    const int sub_r = lane >> 3, col4 = (lane & 7) * 4;
+    uint32_t j = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++j) {
+      int z, m0, n0, kb0, nkb;
+      decode(u, z, m0, n0, kb0, nkb);
+      const uint32_t buf = j & 1;
+      mbar_wait(tfull_bar(buf), (j >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const bool add_bias = ep.bias != nullptr && z == 0;
+      const int row_base = m0 + quarter * 32;
 #pragma unroll 1
-    for (int cc = 0; cc < BN / 32; ++cc) {
-      const int col0 = n0 + cc * 32;
-      if (col0 >= ep.N) break;                    // warp-uniform (N % 32 == 0)
-      uint32_t r[32];
-      if (num_kb > 0) {
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cc * 32), r);
-      } else {
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        const int col0 = n0 + cc * 32;
+        if (col0 >= ep.N) break;                  // warp-uniform (N % 32 == 0)
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + cc * 32), r);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) r[i] = 0u;
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<uint4*>(stg + lane * STG_PITCH + 4 * g) = make_uint4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr) {
+          const int rr = itr * 4 + sub_r;
+          const int row = row_base + rr;
+          const float4 v = *reinterpret_cast<const float4*>(stg + rr * STG_PITCH + col4);
+          if (row < ep.M) epilogue_store4(ep, v, row, col0 + col4, add_bias, key);
+        }
+        __syncwarp();
       }
-      if (row < ep.M) {
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = __uint_as_float(r[i]);
-          if (add_bias) x += __ldg(ep.bias + col0 + i);
-          if (ep.relu) x = fmaxf(x, 0.f);
-          if (ep.use_drop) x *= drop_mult(key, (uint64_t)row * ep.N + col0 + i, ep.drop.thresh, ep.drop.scale);
-          v[i] = x;
-        }
-        if (ep.aux) {
-          const uint4* ap = reinterpret_cast<const uint4*>(ep.aux + (long)row * ep.ld_aux + col0);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 pk = __ldg(ap + g);
-            const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&pk);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[g * 8 + i] = __bfloat162float(hb[i]) > 0.f ? v[g * 8 + i] * ep.aux_scale : 0.f;
-          }
-        }
-        if (ep.out_bf16) {
-          __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(ep.C) + (long)row * ep.ldc + col0;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 pk;
-            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[g * 8 + 0], v[g * 8 + 1]);
-            __nv_bfloat162 t1 = __floats2bfloat162_rn(v[g * 8 + 2], v[g * 8 + 3]);
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[g * 8 + 4], v[g * 8 + 5]);
-            __nv_bfloat162 t3 = __floats2bfloat162_rn(v[g * 8 + 6], v[g * 8 + 7]);
-            pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-            pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-            *reinterpret_cast<uint4*>(cp + g * 8) = pk;
-          }
-        } else {
-          float* cp = reinterpret_cast<float*>(ep.C) + (long)row * ep.ldc + col0;
-          if (ep.split_k > 1) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) atomicAdd(cp + i, v[i]);
-          } else {
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              float4 o = make_float4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-              if (ep.accumulate) {
-                const float4 old = *reinterpret_cast<const float4*>(cp + g * 4);
-                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-              }
-              *reinterpret_cast<float4*>(cp + g * 4) = o;
-            }
-          }
-        }
-      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      if (lane == 0) mbar_arrive(tempty_bar(buf));
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
   }
 }
 
@@ -300,6 +346,38 @@ int encode_2d(CUtensorMap* m, const void* base, long inner, long outer, long ld,
   return MMNAS_OK;
 }
 
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+template <bool A_MN, bool B_MN, int BN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcEpilogue& ep, cudaStream_t s) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    MMNAS_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<A_MN, B_MN, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int units = ep.tiles_m * ep.tiles_n * ep.split_k;
+  const int grid = units < num_sms() ? units : num_sms();
+  gemm_bf16_tc_kernel<A_MN, B_MN, BN><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, s>>>(ta, tb, ep);
+  MMNAS_LAUNCH_CHECK();
+  return MMNAS_OK;
+}
+
+template <int BN>
+int dispatch(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TcEpilogue& ep, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch<false, false, BN>(ta, tb, ep, s);
+  if (!a_mn && b_mn) return launch<false, true, BN>(ta, tb, ep, s);
+  if (a_mn && !b_mn) return launch<true, false, BN>(ta, tb, ep, s);
+  return launch<true, true, BN>(ta, tb, ep, s);
+}
+
 }  // namespace
 
 extern "C" int mmnas_gemm_bf16(int M, int N, int K, const void* A, long lda, int a_mn_major, const void* B, long ldb,
@@ -307,26 +385,38 @@ extern "C" int mmnas_gemm_bf16(int M, int N, int K, const void* A, long lda, int
                                int accumulate, const void* aux, long ld_aux, float aux_scale, int split_k,
                                const unsigned long long* rng_state, unsigned long long salt, float p,
                                mmnas_stream stream) {
-  MMNAS_CHECK_ARG(M >= 0 && N >= 0 && K >= 0, "gemm_bf16: negative size");
+  MMNAS_CHECK_ARG(M >= 0 && N >= 0 && K >= 1, "gemm_bf16: bad size (K must be >= 1)");
   if (M == 0 || N == 0) return MMNAS_OK;
   MMNAS_CHECK_ARG(A && B && C, "gemm_bf16: null operand");
   MMNAS_CHECK_ARG(N % 32 == 0, "gemm_bf16: N must be a multiple of 32");
   MMNAS_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "gemm_bf16: operand pitches must be multiples of 8 elements (16 B)");
   MMNAS_CHECK_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)C % 16) == 0, "gemm_bf16: 16-byte alignment");
   MMNAS_CHECK_ARG(ldc % (out_bf16 ? 8 : 4) == 0, "gemm_bf16: ldc alignment");
+  MMNAS_CHECK_ARG(!bias || ((uintptr_t)bias % 16) == 0, "gemm_bf16: bias alignment");
   if (split_k < 1) split_k = 1;
-  const int kb_total = ceil_div(K > 0 ? K : 1, BK);
+  const int kb_total = ceil_div(K, BK);
   if (split_k > kb_total) split_k = kb_total;
   MMNAS_CHECK_ARG(split_k == 1 || (!out_bf16 && !relu && !aux && !accumulate && !(p > 0.f)),
                   "gemm_bf16: split-K only supports the plain / bias fp32 epilogue");
   MMNAS_CHECK_ARG(!accumulate || !out_bf16, "gemm_bf16: accumulate needs fp32 output");
-  MMNAS_CHECK_ARG(!aux || ld_aux % 8 == 0, "gemm_bf16: aux pitch");
+  MMNAS_CHECK_ARG(!aux || (ld_aux % 8 == 0 && ((uintptr_t)aux % 8) == 0), "gemm_bf16: aux pitch / alignment");
+  int kb_per = ceil_div(kb_total, split_k);
+  split_k = ceil_div(kb_total, kb_per);                 // no empty splits
+  // BN = 256 halves operand traffic per FLOP; take it unless it costs an extra wave (or multiplies split-K atomics)
+  const int tiles_m = ceil_div(M, BM);
+  const int sms = num_sms();
+  int bn = 128;
+  if (split_k == 1 && N % 256 == 0) {
+    const int w128 = ceil_div(tiles_m * ceil_div(N, 128), sms);
+    const int w256 = 2 * ceil_div(tiles_m * ceil_div(N, 256), sms);
+    if (w256 <= w128) bn = 256;
+  }
   CUtensorMap ta, tb;
   int rc;
   if (!a_mn_major) rc = encode_2d(&ta, A, K, M, lda, BK, BM);     // [M rows][K contiguous]
   else rc = encode_2d(&ta, A, M, K, lda, 64, BK);                 // [K rows][M contiguous]
   if (rc) return rc;
-  if (!b_mn_major) rc = encode_2d(&tb, B, K, N, ldb, BK, BN);     // [N rows][K contiguous]
+  if (!b_mn_major) rc = encode_2d(&tb, B, K, N, ldb, BK, bn);     // [N rows][K contiguous]
   else rc = encode_2d(&tb, B, N, K, ldb, 64, BK);                 // [K rows][N contiguous]
   if (rc) return rc;
   TcEpilogue ep = {};
@@ -336,20 +426,8 @@ extern "C" int mmnas_gemm_bf16(int M, int N, int K, const void* A, long lda, int
   ep.use_drop = (p > 0.f && rng_state) ? 1 : 0;
   ep.drop.state = rng_state; ep.drop.salt = salt;
   ep.drop.thresh = (unsigned)(p * 65536.f + 0.5f); ep.drop.scale = p < 1.f ? 1.f / (1.f - p) : 0.f;
-  dim3 grid(ceil_div(N, BN), ceil_div(M, BM), split_k);
+  ep.tiles_m = tiles_m; ep.tiles_n = ceil_div(N, bn); ep.kb_total = kb_total; ep.kb_per = kb_per;
   cudaStream_t s = (cudaStream_t)stream;
-  static bool attr_done = false;
-  if (!attr_done) {
-    MMNAS_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    MMNAS_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    MMNAS_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    MMNAS_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_done = true;
-  }
-  if (!a_mn_major && !b_mn_major) gemm_bf16_tc_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta, tb, ep);
-  else if (!a_mn_major && b_mn_major) gemm_bf16_tc_kernel<false, true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta, tb, ep);
-  else if (a_mn_major && !b_mn_major) gemm_bf16_tc_kernel<true, false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta, tb, ep);
-  else gemm_bf16_tc_kernel<true, true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta, tb, ep);
-  MMNAS_LAUNCH_CHECK();
-  return MMNAS_OK;
+  if (bn == 256) return dispatch<256>(a_mn_major, b_mn_major, ta, tb, ep, s);
+  return dispatch<128>(a_mn_major, b_mn_major, ta, tb, ep, s);
 }

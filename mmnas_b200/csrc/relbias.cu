@@ -4,241 +4,290 @@
 //        = relu(W_y . g_ij + b_y),  g_ij = 4-d box log-geometry (geometry mode: full_vqa.py:82,103
 //          folded in, so the [B,N,N,REL_SIZE] tensor never exists in HBM)
 // Backward accumulates dW_r, db_r (and dW_y, db_y in geometry mode; d rel_embed in dense mode) from
-// dbias = dS of the attention backward.  Thread per (i,j) pair for the pointwise part; the weight
-// gradients are small GEMM-shaped reductions over the pairs, done per 256-pair tile in shared
-// memory with per-thread register accumulators across a persistent grid (one global atomic per
-// output per CTA).
+// dbias = dS of the attention backward.
+//
+// Design (v2).  The layer weights (<= 5.5 KB) are staged into __constant__ memory per call, so the fully
+// unrolled per-pair MLP uses FFMA with constant-bank operands: no weight loads at all.  Forward: one thread per
+// (i,j) pair, no shared memory.  Backward: 128-pair tiles; phase A (thread = pair) recomputes e, r and the
+// chain rule and parks e / d pre_e transposed in shared memory ([c][pair], padded so both the scalar writes of
+// phase A and the 128-bit reads of phase B are bank-conflict free); phase B (thread = column c, two half-tiles)
+// reduces the tile into 13 register accumulators per thread (dW_r[:,c], dW_y[c,:], db_y[c]) with a two-level
+// sum; one global atomic per output per CTA at the end.  Persistent grid of 3 CTAs per SM.
+// The constant staging makes these entry points single-stream per device (calls are stream-ordered).
 #include "common.cuh"
 #include "../../include/mmnas_b200.h"
 
 namespace {
 
 constexpr int MAXH = 16;     // heads
-constexpr int MAXR = 64;     // REL_SIZE
-constexpr int TILE = 256;    // pairs per tile == threads per CTA
+constexpr int R = 64;        // REL_SIZE
+constexpr int TILE = 128;    // pairs per tile == threads per CTA
+constexpr int EP = TILE + 4; // padded pair pitch of the transposed tiles
+
+__constant__ float cWy[R * 4];
+__constant__ float cby[R];
+__constant__ float cWr[MAXH * R];
+__constant__ float cbr[MAXH];
 
 struct RelArgs {
-  int B, N, heads, R;
-  long pairs;
+  int B, N, heads;
+  unsigned pairs, nn;
   const float* rel;     // dense: [pairs, R]
   const float* g4;      // geometry: [pairs, 4]
-  const float *Wy, *by; // [R,4], [R]
-  const float *Wr, *br; // [heads,R], [heads]
   float* bias;          // [B, heads, N, N]
   const float* dbias;
   float* drel;
   float *dWy, *dby, *dWr, *dbr;
 };
 
-__device__ __forceinline__ long bias_index(const RelArgs& a, long pair, int hh) {
-  const long nn = (long)a.N * a.N;
-  const long b = pair / nn, ij = pair % nn;
-  return (b * a.heads + hh) * nn + ij;
-}
-
-template <bool DENSE>
-__global__ void __launch_bounds__(TILE) relbias_fwd_kernel(RelArgs a) {
-  __shared__ float sWr[MAXH * MAXR], sbr[MAXH], sWy[MAXR * 4], sby[MAXR];
-  for (int i = threadIdx.x; i < a.heads * a.R; i += TILE) sWr[i] = a.Wr[i];
-  for (int i = threadIdx.x; i < a.heads; i += TILE) sbr[i] = a.br[i];
-  if (!DENSE) {
-    for (int i = threadIdx.x; i < a.R * 4; i += TILE) sWy[i] = a.Wy[i];
-    for (int i = threadIdx.x; i < a.R; i += TILE) sby[i] = a.by[i];
-  }
-  __syncthreads();
-  const long pair = (long)blockIdx.x * TILE + threadIdx.x;
+template <int HEADS, bool DENSE>
+__global__ void __launch_bounds__(256) relbias_fwd_kernel(RelArgs a) {
+  const unsigned pair = blockIdx.x * 256u + threadIdx.x;
   if (pair >= a.pairs) return;
-  float r[MAXH];
+  float r[HEADS];
 #pragma unroll
-  for (int hh = 0; hh < MAXH; ++hh) r[hh] = 0.f;
-  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (!DENSE) g = *reinterpret_cast<const float4*>(a.g4 + pair * 4);
-  for (int c = 0; c < a.R; ++c) {
-    float e;
-    if (DENSE) e = a.rel[pair * a.R + c];
-    else e = fmaxf(fmaf(sWy[c * 4 + 0], g.x, fmaf(sWy[c * 4 + 1], g.y, fmaf(sWy[c * 4 + 2], g.z, fmaf(sWy[c * 4 + 3], g.w, sby[c])))), 0.f);
+  for (int h = 0; h < HEADS; ++h) r[h] = cbr[h];
+  if (DENSE) {
+    const float4* e4 = reinterpret_cast<const float4*>(a.rel + (size_t)pair * R);
 #pragma unroll
-    for (int hh = 0; hh < MAXH; ++hh)
-      if (hh < a.heads) r[hh] = fmaf(sWr[hh * a.R + c], e, r[hh]);
+    for (int c4 = 0; c4 < R / 4; ++c4) {
+      const float4 e = __ldg(e4 + c4);
+#pragma unroll
+      for (int h = 0; h < HEADS; ++h) {
+        r[h] = fmaf(cWr[h * R + 4 * c4 + 0], e.x, r[h]);
+        r[h] = fmaf(cWr[h * R + 4 * c4 + 1], e.y, r[h]);
+        r[h] = fmaf(cWr[h * R + 4 * c4 + 2], e.z, r[h]);
+        r[h] = fmaf(cWr[h * R + 4 * c4 + 3], e.w, r[h]);
+      }
+    }
+  } else {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(a.g4) + pair);
+#pragma unroll
+    for (int c = 0; c < R; ++c) {
+      const float e = fmaxf(fmaf(cWy[c * 4 + 0], g.x, fmaf(cWy[c * 4 + 1], g.y, fmaf(cWy[c * 4 + 2], g.z, fmaf(cWy[c * 4 + 3], g.w, cby[c])))), 0.f);
+#pragma unroll
+      for (int h = 0; h < HEADS; ++h) r[h] = fmaf(cWr[h * R + c], e, r[h]);
+    }
   }
+  const unsigned b = pair / a.nn, ij = pair - b * a.nn;
+  float* out = a.bias + ((size_t)b * HEADS) * a.nn + ij;
 #pragma unroll
-  for (int hh = 0; hh < MAXH; ++hh)
-    if (hh < a.heads) a.bias[bias_index(a, pair, hh)] = logf(fmaxf(fmaxf(r[hh] + sbr[hh], 0.f), 1e-6f));
+  for (int h = 0; h < HEADS; ++h) out[(size_t)h * a.nn] = logf(fmaxf(fmaxf(r[h], 0.f), 1e-6f));
 }
 
-template <bool DENSE>
+template <int HEADS, bool DENSE>
 __global__ void __launch_bounds__(TILE) relbias_bwd_kernel(RelArgs a) {
   extern __shared__ float sm[];
-  float* sWr = sm;                       // [heads][R]
-  float* sbr = sWr + MAXH * MAXR;        // [heads]
-  float* sWy = sbr + MAXH;               // [R][4]
-  float* sby = sWy + MAXR * 4;           // [R]
-  float* E = sby + MAXR;                 // [TILE][R]    e (post-ReLU in geometry mode)
-  float* DE = E + TILE * MAXR;           // [TILE][R]    d pre_e (geometry) / d rel (dense)
-  float* Dp = DE + TILE * MAXR;          // [TILE][MAXH] d pre_r
-  float* G = Dp + TILE * MAXH;           // [TILE][4]
-  const int t = threadIdx.x, R = a.R, heads = a.heads;
-  for (int i = t; i < heads * R; i += TILE) sWr[i] = a.Wr[i];
-  for (int i = t; i < heads; i += TILE) sbr[i] = a.br[i];
-  if (!DENSE) {
-    for (int i = t; i < R * 4; i += TILE) sWy[i] = a.Wy[i];
-    for (int i = t; i < R; i += TILE) sby[i] = a.by[i];
-  }
-  // register accumulators: dWr[(t/64) + 4k][t%64] for k<4, dWy[t%64][t/64], dby[t] (t<R), dbr[t] (t<heads)
-  float accWr[4] = {0.f, 0.f, 0.f, 0.f}, accWy = 0.f, accby = 0.f, accbr = 0.f;
-  const int c_own = t % 64, q_own = t / 64;
-  const long ntiles = (a.pairs + TILE - 1) / TILE;
-  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  float* E = sm;                     // [R][EP]   e, transposed
+  float* DE = E + R * EP;            // [R][EP]   d pre_e (geometry) / d rel (dense), transposed
+  float* Dp = DE + R * EP;           // [TILE][HP] d pre_r
+  constexpr int HP = HEADS < 4 ? 4 : HEADS;
+  float* G = Dp + TILE * HP;         // [TILE][4]
+  const int t = threadIdx.x;
+  const int c_own = t & 63, half = t >> 6;      // phase B: column and which half of the tile's pairs
+  float accWr[HEADS], accWy[4] = {0.f, 0.f, 0.f, 0.f}, accby = 0.f, accbr = 0.f;
+#pragma unroll
+  for (int h = 0; h < HEADS; ++h) accWr[h] = 0.f;
+  const unsigned ntiles = (a.pairs + TILE - 1) / TILE;
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     __syncthreads();
-    const long pair = tile * TILE + t;
+    // ---------------- phase A: thread = pair
+    const unsigned pair = tile * TILE + t;
     const bool live = pair < a.pairs;
-    // ---- phase A: pointwise recompute + chain rule for this thread's pair
-    if (DENSE) {   // coalesced tile load of rel
-      const long base = tile * TILE * (long)R;
-      const long lim = a.pairs * (long)R;
-      for (int e = t; e < TILE * R; e += TILE) E[e] = (base + e < lim) ? a.rel[base + e] : 0.f;
-      __syncthreads();
-    }
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!DENSE && live) g = *reinterpret_cast<const float4*>(a.g4 + pair * 4);
-    float r[MAXH];
+    float r[HEADS];
 #pragma unroll
-    for (int hh = 0; hh < MAXH; ++hh) r[hh] = 0.f;
-    // E is written/read by its owner thread with a rotated column order so lanes hit distinct banks
-    for (int cc = 0; cc < R; ++cc) {
-      const int c = DENSE ? cc : ((cc + t) & (R - 1));
-      float e;
-      if (DENSE) e = E[t * R + ((cc + t) & (R - 1))];
-      else {
-        e = fmaxf(fmaf(sWy[c * 4 + 0], g.x, fmaf(sWy[c * 4 + 1], g.y, fmaf(sWy[c * 4 + 2], g.z, fmaf(sWy[c * 4 + 3], g.w, sby[c])))), 0.f);
-        E[t * R + c] = live ? e : 0.f;
+    for (int h = 0; h < HEADS; ++h) r[h] = cbr[h];
+    if (DENSE) {
+      const float4* e4 = reinterpret_cast<const float4*>(a.rel + (size_t)pair * R);
+#pragma unroll
+      for (int c4 = 0; c4 < R / 4; ++c4) {
+        const float4 e = live ? __ldg(e4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        E[(4 * c4 + 0) * EP + t] = e.x; E[(4 * c4 + 1) * EP + t] = e.y;
+        E[(4 * c4 + 2) * EP + t] = e.z; E[(4 * c4 + 3) * EP + t] = e.w;
+#pragma unroll
+        for (int h = 0; h < HEADS; ++h) {
+          r[h] = fmaf(cWr[h * R + 4 * c4 + 0], e.x, r[h]);
+          r[h] = fmaf(cWr[h * R + 4 * c4 + 1], e.y, r[h]);
+          r[h] = fmaf(cWr[h * R + 4 * c4 + 2], e.z, r[h]);
+          r[h] = fmaf(cWr[h * R + 4 * c4 + 3], e.w, r[h]);
+        }
       }
-      const int cw = DENSE ? ((cc + t) & (R - 1)) : c;
+    } else {
+      if (live) g = __ldg(reinterpret_cast<const float4*>(a.g4) + pair);
 #pragma unroll
-      for (int hh = 0; hh < MAXH; ++hh)
-        if (hh < heads) r[hh] = fmaf(sWr[hh * R + cw], e, r[hh]);
-    }
-    float dpre[MAXH];
+      for (int c = 0; c < R; ++c) {
+        float e = fmaxf(fmaf(cWy[c * 4 + 0], g.x, fmaf(cWy[c * 4 + 1], g.y, fmaf(cWy[c * 4 + 2], g.z, fmaf(cWy[c * 4 + 3], g.w, cby[c])))), 0.f);
+        e = live ? e : 0.f;
+        E[c * EP + t] = e;
 #pragma unroll
-    for (int hh = 0; hh < MAXH; ++hh) {
-      dpre[hh] = 0.f;
-      if (hh < heads && live) {
-        const float rv = r[hh] + sbr[hh];
-        if (rv > 1e-6f) dpre[hh] = a.dbias[bias_index(a, pair, hh)] / rv;   // clamp & relu both pass
+        for (int h = 0; h < HEADS; ++h) r[h] = fmaf(cWr[h * R + c], e, r[h]);
       }
-      if (hh < heads) Dp[t * MAXH + hh] = dpre[hh];
+      *reinterpret_cast<float4*>(G + t * 4) = g;
     }
-    for (int cc = 0; cc < R; ++cc) {
-      const int c = (cc + t) & (R - 1);
+    float dpre[HEADS];
+    {
+      const unsigned b = live ? pair / a.nn : 0u, ij = live ? pair - b * a.nn : 0u;
+      const float* db = a.dbias + ((size_t)b * HEADS) * a.nn + ij;
+#pragma unroll
+      for (int h = 0; h < HEADS; ++h) {
+        dpre[h] = (live && r[h] > 1e-6f) ? __ldg(db + (size_t)h * a.nn) / r[h] : 0.f;   // relu and clamp both pass
+        Dp[t * HP + h] = dpre[h];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < R; ++c) {
       float de = 0.f;
 #pragma unroll
-      for (int hh = 0; hh < MAXH; ++hh)
-        if (hh < heads) de = fmaf(sWr[hh * R + c], dpre[hh], de);
-      if (!DENSE) de = E[t * R + c] > 0.f ? de : 0.f;
-      DE[t * R + c] = de;
+      for (int h = 0; h < HEADS; ++h) de = fmaf(cWr[h * R + c], dpre[h], de);
+      if (!DENSE) de = E[c * EP + t] > 0.f ? de : 0.f;
+      DE[c * EP + t] = de;
     }
-    if (!DENSE) *reinterpret_cast<float4*>(G + t * 4) = g;
     __syncthreads();
-    if (DENSE) {   // coalesced store of d rel_embed
-      const long base = tile * TILE * (long)R;
-      const long lim = a.pairs * (long)R;
-      for (int e = t; e < TILE * R; e += TILE)
-        if (base + e < lim) a.drel[base + e] = DE[e];
-    }
-    // ---- phase B: reductions over the tile's pairs.  Two-level summation (tile-local partials, then the
-    // running total) keeps fp32 round-off at the level of a blocked GEMM instead of a 70k-term serial sum.
-    float pWr[4] = {0.f, 0.f, 0.f, 0.f}, pWy = 0.f, pby = 0.f, pbr = 0.f;
-    for (int p = 0; p < TILE; ++p) {
-      const float ev = E[p * R + c_own];
+    if (DENSE && live) {      // d rel_embed row of this pair
+      float4* o4 = reinterpret_cast<float4*>(a.drel + (size_t)pair * R);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int hh = q_own + 4 * k;
-        if (hh < heads) pWr[k] = fmaf(Dp[p * MAXH + hh], ev, pWr[k]);
-      }
+      for (int c4 = 0; c4 < R / 4; ++c4)
+        o4[c4] = make_float4(DE[(4 * c4 + 0) * EP + t], DE[(4 * c4 + 1) * EP + t], DE[(4 * c4 + 2) * EP + t],
+                             DE[(4 * c4 + 3) * EP + t]);
+    }
+    // ---------------- phase B: thread = column c_own over its half of the pairs; two-level summation
+    float pWr[HEADS], pWy[4] = {0.f, 0.f, 0.f, 0.f}, pby = 0.f, pbr = 0.f;
+#pragma unroll
+    for (int h = 0; h < HEADS; ++h) pWr[h] = 0.f;
+    const int p0 = half * (TILE / 2);
+#pragma unroll 2
+    for (int p = p0; p < p0 + TILE / 2; p += 4) {
+      const float4 ev = *reinterpret_cast<const float4*>(E + c_own * EP + p);
+      const float ee[4] = {ev.x, ev.y, ev.z, ev.w};
+      float dd[4] = {0.f, 0.f, 0.f, 0.f};
       if (!DENSE) {
-        const float dev = DE[p * R + c_own];
-        pWy = fmaf(dev, G[p * 4 + q_own], pWy);
-        if (q_own == 0) pby += dev;
+        const float4 dv = *reinterpret_cast<const float4*>(DE + c_own * EP + p);
+        dd[0] = dv.x; dd[1] = dv.y; dd[2] = dv.z; dd[3] = dv.w;
       }
-      if (t < heads) pbr += Dp[p * MAXH + t];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int h = 0; h < HEADS; ++h) pWr[h] = fmaf(Dp[(p + u) * HP + h], ee[u], pWr[h]);
+        if (!DENSE) {
+          const float4 gv = *reinterpret_cast<const float4*>(G + (p + u) * 4);
+          pWy[0] = fmaf(dd[u], gv.x, pWy[0]); pWy[1] = fmaf(dd[u], gv.y, pWy[1]);
+          pWy[2] = fmaf(dd[u], gv.z, pWy[2]); pWy[3] = fmaf(dd[u], gv.w, pWy[3]);
+          pby += dd[u];
+        }
+        if (c_own < HEADS) pbr += Dp[(p + u) * HP + c_own];
+      }
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) accWr[k] += pWr[k];
-    accWy += pWy; accby += pby; accbr += pbr;
-  }
-  if (c_own < R) {
+    for (int h = 0; h < HEADS; ++h) accWr[h] += pWr[h];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int hh = q_own + 4 * k;
-      if (hh < heads) atomicAdd(&a.dWr[hh * R + c_own], accWr[k]);
-    }
-    if (!DENSE) {
-      atomicAdd(&a.dWy[c_own * 4 + q_own], accWy);
-      if (q_own == 0) atomicAdd(&a.dby[c_own], accby);
-    }
+    for (int k = 0; k < 4; ++k) accWy[k] += pWy[k];
+    accby += pby; accbr += pbr;
   }
-  if (t < heads) atomicAdd(&a.dbr[t], accbr);
+#pragma unroll
+  for (int h = 0; h < HEADS; ++h) atomicAdd(&a.dWr[h * R + c_own], accWr[h]);
+  if (!DENSE) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) atomicAdd(&a.dWy[c_own * 4 + k], accWy[k]);
+    atomicAdd(&a.dby[c_own], accby);
+  }
+  if (c_own < HEADS) atomicAdd(&a.dbr[c_own], accbr);
 }
 
-size_t bwd_smem_bytes() {
-  return sizeof(float) * (MAXH * MAXR + MAXH + MAXR * 4 + MAXR + 2 * TILE * MAXR + TILE * MAXH + TILE * 4);
+template <int HEADS>
+constexpr size_t bwd_smem_bytes() {
+  return sizeof(float) * (2 * R * EP + TILE * (HEADS < 4 ? 4 : HEADS) + TILE * 4);
 }
 
-int check(int B, int N, int heads, int R, const float* rel, const float* g4, const float* Wy, const float* by,
+int check(int B, int N, int heads, int Rin, const float* rel, const float* g4, const float* Wy, const float* by,
           const float* Wr, const float* br) {
   MMNAS_CHECK_ARG(B >= 0 && N > 0, "relbias: bad sizes");
-  MMNAS_CHECK_ARG(heads >= 1 && heads <= MAXH, "relbias: heads must be in [1,16]");
-  MMNAS_CHECK_ARG(R == MAXR, "relbias: REL_SIZE must be 64");
+  MMNAS_CHECK_ARG(heads == 1 || heads == 2 || heads == 4 || heads == 8 || heads == 16, "relbias: heads must be 1, 2, 4, 8 or 16");
+  MMNAS_CHECK_ARG(Rin == R, "relbias: REL_SIZE must be 64");
   MMNAS_CHECK_ARG((rel != nullptr) != (g4 != nullptr), "relbias: give exactly one of rel_embed / geometry");
   MMNAS_CHECK_ARG(!g4 || (Wy && by), "relbias: geometry mode needs linear_y_rel weights");
   MMNAS_CHECK_ARG(Wr && br, "relbias: linear_r weights missing");
+  MMNAS_CHECK_ARG((double)B * N * N < 4.0e9, "relbias: too many pairs");
   return MMNAS_OK;
 }
 
-}  // namespace
+int stage_weights(int heads, const float* Wy, const float* by, const float* Wr, const float* br, cudaStream_t s) {
+  if (Wy) {
+    MMNAS_CUDA(cudaMemcpyToSymbolAsync(cWy, Wy, sizeof(float) * R * 4, 0, cudaMemcpyDeviceToDevice, s));
+    MMNAS_CUDA(cudaMemcpyToSymbolAsync(cby, by, sizeof(float) * R, 0, cudaMemcpyDeviceToDevice, s));
+  }
+  MMNAS_CUDA(cudaMemcpyToSymbolAsync(cWr, Wr, sizeof(float) * heads * R, 0, cudaMemcpyDeviceToDevice, s));
+  MMNAS_CUDA(cudaMemcpyToSymbolAsync(cbr, br, sizeof(float) * heads, 0, cudaMemcpyDeviceToDevice, s));
+  return MMNAS_OK;
+}
 
-extern "C" int mmnas_relbias_fwd(int B, int N, int heads, int R, const float* rel, const float* g4, const float* Wy,
-                                 const float* by, const float* Wr, const float* br, float* bias,
-                                 mmnas_stream stream) {
-  int rc = check(B, N, heads, R, rel, g4, Wy, by, Wr, br);
-  if (rc) return rc;
-  if (B == 0) return MMNAS_OK;
-  MMNAS_CHECK_ARG(bias, "relbias_fwd: null output");
-  RelArgs a = {};
-  a.B = B; a.N = N; a.heads = heads; a.R = R; a.pairs = (long)B * N * N;
-  a.rel = rel; a.g4 = g4; a.Wy = Wy; a.by = by; a.Wr = Wr; a.br = br; a.bias = bias;
-  const int grid = (int)((a.pairs + TILE - 1) / TILE);
-  if (rel) relbias_fwd_kernel<true><<<grid, TILE, 0, (cudaStream_t)stream>>>(a);
-  else relbias_fwd_kernel<false><<<grid, TILE, 0, (cudaStream_t)stream>>>(a);
+template <int HEADS>
+int launch_fwd(const RelArgs& a, cudaStream_t s) {
+  const unsigned grid = (a.pairs + 255u) / 256u;
+  if (a.rel) relbias_fwd_kernel<HEADS, true><<<grid, 256, 0, s>>>(a);
+  else relbias_fwd_kernel<HEADS, false><<<grid, 256, 0, s>>>(a);
   MMNAS_LAUNCH_CHECK();
   return MMNAS_OK;
 }
 
-extern "C" int mmnas_relbias_bwd(int B, int N, int heads, int R, const float* rel, const float* g4, const float* Wy,
+template <int HEADS>
+int launch_bwd(const RelArgs& a, cudaStream_t s) {
+  constexpr size_t smem = bwd_smem_bytes<HEADS>();
+  static bool attr_done = false;
+  if (!attr_done) {
+    MMNAS_CUDA(cudaFuncSetAttribute(relbias_bwd_kernel<HEADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMNAS_CUDA(cudaFuncSetAttribute(relbias_bwd_kernel<HEADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  const unsigned ntiles = (a.pairs + TILE - 1) / TILE;
+  const unsigned grid = ntiles < 148u * 3u ? ntiles : 148u * 3u;
+  if (a.rel) relbias_bwd_kernel<HEADS, true><<<grid, TILE, smem, s>>>(a);
+  else relbias_bwd_kernel<HEADS, false><<<grid, TILE, smem, s>>>(a);
+  MMNAS_LAUNCH_CHECK();
+  return MMNAS_OK;
+}
+
+#define DISPATCH_HEADS(FN, heads, ...)            \
+  switch (heads) {                                \
+    case 1: return FN<1>(__VA_ARGS__);            \
+    case 2: return FN<2>(__VA_ARGS__);            \
+    case 4: return FN<4>(__VA_ARGS__);            \
+    case 8: return FN<8>(__VA_ARGS__);            \
+    default: return FN<16>(__VA_ARGS__);          \
+  }
+
+}  // namespace
+
+extern "C" int mmnas_relbias_fwd(int B, int N, int heads, int Rin, const float* rel, const float* g4, const float* Wy,
+                                 const float* by, const float* Wr, const float* br, float* bias,
+                                 mmnas_stream stream) {
+  int rc = check(B, N, heads, Rin, rel, g4, Wy, by, Wr, br);
+  if (rc) return rc;
+  if (B == 0) return MMNAS_OK;
+  MMNAS_CHECK_ARG(bias, "relbias_fwd: null output");
+  cudaStream_t s = (cudaStream_t)stream;
+  rc = stage_weights(heads, g4 ? Wy : nullptr, by, Wr, br, s);
+  if (rc) return rc;
+  RelArgs a = {};
+  a.B = B; a.N = N; a.heads = heads; a.nn = (unsigned)N * N; a.pairs = (unsigned)B * a.nn;
+  a.rel = rel; a.g4 = g4; a.bias = bias;
+  DISPATCH_HEADS(launch_fwd, heads, a, s)
+}
+
+extern "C" int mmnas_relbias_bwd(int B, int N, int heads, int Rin, const float* rel, const float* g4, const float* Wy,
                                  const float* by, const float* Wr, const float* br, const float* dbias, float* drel,
                                  float* dWy, float* dby, float* dWr, float* dbr, mmnas_stream stream) {
-  int rc = check(B, N, heads, R, rel, g4, Wy, by, Wr, br);
+  int rc = check(B, N, heads, Rin, rel, g4, Wy, by, Wr, br);
   if (rc) return rc;
   if (B == 0) return MMNAS_OK;
   MMNAS_CHECK_ARG(dbias && dWr && dbr, "relbias_bwd: null buffer");
   MMNAS_CHECK_ARG(!rel || drel, "relbias_bwd: dense mode needs d rel_embed output");
   MMNAS_CHECK_ARG(!g4 || (dWy && dby), "relbias_bwd: geometry mode needs dWy/dby outputs");
-  RelArgs a = {};
-  a.B = B; a.N = N; a.heads = heads; a.R = R; a.pairs = (long)B * N * N;
-  a.rel = rel; a.g4 = g4; a.Wy = Wy; a.by = by; a.Wr = Wr; a.br = br;
-  a.dbias = dbias; a.drel = drel; a.dWy = dWy; a.dby = dby; a.dWr = dWr; a.dbr = dbr;
-  const long ntiles = (a.pairs + TILE - 1) / TILE;
-  const int grid = (int)(ntiles < 148 ? ntiles : 148);
-  const size_t smem = bwd_smem_bytes();
   cudaStream_t s = (cudaStream_t)stream;
-  static bool attr_done = false;
-  if (!attr_done) {
-    MMNAS_CUDA(cudaFuncSetAttribute(relbias_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MMNAS_CUDA(cudaFuncSetAttribute(relbias_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
-  if (rel) relbias_bwd_kernel<true><<<grid, TILE, smem, s>>>(a);
-  else relbias_bwd_kernel<false><<<grid, TILE, smem, s>>>(a);
-  MMNAS_LAUNCH_CHECK();
-  return MMNAS_OK;
+  rc = stage_weights(heads, g4 ? Wy : nullptr, by, Wr, br, s);
+  if (rc) return rc;
+  RelArgs a = {};
+  a.B = B; a.N = N; a.heads = heads; a.nn = (unsigned)N * N; a.pairs = (unsigned)B * a.nn;
+  a.rel = rel; a.g4 = g4; a.dbias = dbias; a.drel = drel; a.dWy = dWy; a.dby = dby; a.dWr = dWr; a.dbr = dbr;
+  DISPATCH_HEADS(launch_bwd, heads, a, s)
 }

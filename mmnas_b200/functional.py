@@ -34,10 +34,11 @@ class BlockCfg:
 
 
 def _split_k(M, N, K):
+    """Split the token reduction of a weight-gradient GEMM so that (#output tiles x splits) ~ one wave of 148
+    SMs, keeping at least 4 k-blocks of 64 per split."""
     tiles = ((M + 127) // 128) * ((N + 127) // 128)
     kb = (K + 63) // 64
-    s = max(1, min((2 * 148 + tiles - 1) // tiles, kb // 4 if kb >= 4 else 1))
-    return s
+    return max(1, min(148 // tiles if tiles <= 148 else 1, kb // 4 if kb >= 4 else 1))
 
 
 def _empty(shape, dtype, dev):

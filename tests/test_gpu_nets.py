@@ -135,6 +135,11 @@ def test_net_full_vqa_at_baseline_config_matches_oracle(mode, regime):
         tol = GTOL[mode]
         if regime == 'default_init':
             tol = None if is_geometry_param(n_) else max(tol, 5e-3)
+        elif mode == 'fp32' and ('mlp.fc.linear' in n_ or n_.endswith('linear_r.bias')):
+            # a ReLU whose pre-activation is within float32 rounding of 0 takes the other branch than in the
+            # float64 oracle (about one unit per FFN block at these sizes) and moves one token's contribution to
+            # dW1 / db1; linear_r.bias is the cancelling sum described in test_gpu_blocks
+            tol = 1e-3
         pr.add(n_, p_.grad, ref, tol, floor, metric=GMETRIC[mode])
     pr.check()
 
