@@ -1,0 +1,92 @@
+"""Host-side data-parallel logic (FlatGrads + BucketReducer + WarmupAdam) on CPU with the gloo backend, world size 2:
+averaged gradients must equal the single-process gradients of the concatenated batch (sum-reduced loss / world),
+which is DDP's semantics in train_vqa.py:236."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mmnas_b200.engine import FlatGrads, BucketReducer, WarmupAdam
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _model():
+    torch.manual_seed(0)
+    return torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.ReLU(), torch.nn.Linear(32, 32), torch.nn.ReLU(),
+                               torch.nn.Linear(32, 4), torch.nn.Linear(4, 4))   # last layer stays unused below
+
+
+def _forward(m, x):
+    return m[4](m[3](m[2](m[1](m[0](x)))))      # m[5] never runs: its grads must still arrive as zeros
+
+
+def _worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        m = _model()
+        fg = FlatGrads(m.parameters())
+        red = BucketReducer(fg, bucket_mb=0.0004)          # tiny buckets -> several all-reduces
+        assert len(red.buckets) > 2
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(8, 16, generator=g)
+        y = torch.randn(8, 4, generator=g)
+        xs, ys = x[rank * 4:(rank + 1) * 4], y[rank * 4:(rank + 1) * 4]
+        for _ in range(2):                                  # second pass checks re-arming
+            fg.zero()
+            red.reset()
+            loss = ((_forward(m, xs) - ys) ** 2).sum()
+            loss.backward()
+            red.finish()
+        q.put((rank, fg.flat.clone()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_bucket_reducer_matches_single_process_gradients():
+    world, port = 2, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=100) for _ in range(world))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    m = _model()
+    fg = FlatGrads(m.parameters())
+    g = torch.Generator().manual_seed(1)
+    x, y = torch.randn(8, 16, generator=g), torch.randn(8, 4, generator=g)
+    fg.zero()
+    (((_forward(m, x) - y) ** 2).sum() / world).backward()
+    assert torch.allclose(got[0], got[1])
+    assert torch.allclose(got[0], fg.flat, rtol=1e-5, atol=1e-6)
+    unused = fg.view(len(fg.params) - 1)
+    assert float(unused.abs().max()) == 0.0                 # the unused layer received a (zero) gradient
+
+
+def test_flat_grads_survive_grad_none_and_warmup_schedule():
+    m = _model()
+    fg = FlatGrads(m.parameters())
+    for p in m.parameters():
+        p.grad = None                                       # what MixedOp.binarize() does to candidate params
+    fg.zero()
+    assert all(p.grad is not None and p.grad.data_ptr() == fg.view(i).data_ptr() for i, p in enumerate(fg.params))
+    opt = WarmupAdam(m.parameters(), lr_base=1.0, epoch_steps=10)
+    rates = [opt.rate(s) for s in (1, 10, 11, 20, 21, 30, 31, 1000)]
+    assert rates == [0.25, 0.25, 0.5, 0.5, 0.75, 0.75, 1.0, 1.0]      # optimizer.py:25-44
+    opt.decay(0.2)
+    assert abs(opt.rate(1000) - 0.2) < 1e-12

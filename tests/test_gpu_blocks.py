@@ -118,7 +118,7 @@ def test_block_matches_oracle_at_baseline_shapes(name, mode, h, nx, ny, regime):
         # default-init RSA: geometry-path gradients are chaotic in float32 (condition_rsa_ docstring): logged only
         tol = None if (regime == 'default_init' and is_geometry_param(n_)) else GTOL[mode]
         if tol is not None and n_.endswith('linear_r.bias'):
-            tol *= 5      # sum_j dS_ij = 0 per query row, so sum(dS / r) is a cancelling sum even when conditioned
+            tol *= 10     # sum_j dS_ij = 0 per query row, so sum(dS / r) is a cancelling sum even when conditioned
         pr.add(n_, p_.grad, P[n_].grad, tol, metric=gm)
     if name == 'rel_self_att_64':
         tol = None if regime == 'default_init' else GTOL[mode]
