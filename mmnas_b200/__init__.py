@@ -19,29 +19,32 @@ __version__ = '0.1.0'
 
 def install_as_mmnas(include_nets=False):
     """Alias the drop-in modules under the reference's package name.  Call before importing reference code.
-    With include_nets=True, `mmnas.model.full_vqa` / `hygr_vqa` also resolve to this package's nets."""
+
+    If the reference package `mmnas` is importable (its checkout is on sys.path) it is kept, and only
+    `mmnas.model.modules`, `mmnas.model.mixed` and `mmnas.utils.ops_adapter` are replaced, so the reference's own
+    full_*.py / hygr_*.py / train / search code runs on the CUDA operators.  Without the reference, a synthetic
+    `mmnas` package is created.  With include_nets=True, `mmnas.model.full_*` / `hygr_*` also resolve to this
+    package's nets."""
+    import importlib
     from .model import modules, mixed, nets
     from .utils import ops_adapter
-    root = sys.modules.get('mmnas')
-    if root is None or getattr(root, '__mmnas_b200__', False) is False:
-        root = types.ModuleType('mmnas')
-        root.__path__ = []
-        root.__mmnas_b200__ = True
-        sys.modules['mmnas'] = root
-    for pkg in ('mmnas.model', 'mmnas.utils'):
-        if pkg not in sys.modules or not getattr(sys.modules[pkg], '__mmnas_b200__', False):
+    pkgs = {}
+    for pkg in ('mmnas', 'mmnas.model', 'mmnas.utils'):
+        try:
+            pkgs[pkg] = importlib.import_module(pkg)
+        except ImportError:
             m = types.ModuleType(pkg)
             m.__path__ = []
-            m.__mmnas_b200__ = True
             sys.modules[pkg] = m
-            setattr(root, pkg.split('.')[1], m)
-    sys.modules['mmnas.model.modules'] = modules
-    sys.modules['mmnas.model.mixed'] = mixed
-    sys.modules['mmnas.utils.ops_adapter'] = ops_adapter
-    sys.modules['mmnas.model'].modules = modules
-    sys.modules['mmnas.model'].mixed = mixed
-    sys.modules['mmnas.utils'].ops_adapter = ops_adapter
+            pkgs[pkg] = m
+            if '.' in pkg:
+                setattr(pkgs['mmnas'], pkg.split('.')[1], m)
+    for full, mod in (('mmnas.model.modules', modules), ('mmnas.model.mixed', mixed),
+                      ('mmnas.utils.ops_adapter', ops_adapter)):
+        sys.modules[full] = mod
+        parent, leaf = full.rsplit('.', 1)
+        setattr(pkgs[parent], leaf, mod)
     if include_nets:
         for name in ('full_vqa', 'full_vgd', 'full_itm', 'hygr_vqa', 'hygr_vgd', 'hygr_itm'):
             sys.modules['mmnas.model.' + name] = nets
-            setattr(sys.modules['mmnas.model'], name, nets)
+            setattr(pkgs['mmnas.model'], name, nets)

@@ -17,6 +17,7 @@ import torch.nn.functional as F
 
 from .. import kernels as K
 from .. import runtime
+from .._lib import require_cuda
 from ..functional import AttBlockFn, FFNBlockFn, LayerNormFn, BlockCfg
 
 
@@ -175,6 +176,7 @@ class MHAtt(_OpBase):
 
     def run_block(self, x, kv, mask, rel_embed, ln, residual, out_p):
         """Whole block: LN(x + dropout(self(kv, kv, x)))  — one autograd node, CUDA only."""
+        require_cuda(x, kv)
         if self.HBASE != 64:
             raise NotImplementedError("only the '*_64' attention operators (head dim 64) are implemented in CUDA")
         self_att = kv is None or kv is x
@@ -275,6 +277,7 @@ class FeedForward(_OpBase):
         self._init_runtime(2)     # sites: hidden activation, block output
 
     def forward(self, x, y=None, x_mask=None, y_mask=None, rel_embed=None):
+        require_cuda(x)
         mode = self._mode()
         w1, w2 = self.mlp.fc.linear, self.mlp.linear
         w16 = {}
