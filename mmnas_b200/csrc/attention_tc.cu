@@ -1,0 +1,405 @@
+// Attention core on the 5th-gen tensor cores (bf16 arm).  One CTA (128 threads) per (sample, head):
+//   forward   S = Q K^T          (tcgen05.mma 128 x N1 x 64, accumulator in TMEM columns [0,128))
+//             softmax: thread i owns query row i == TMEM lane i, so row max / sum are thread-local (no shuffles);
+//             logits are read twice from TMEM (max pass, exp pass) instead of living in 128 registers
+//             P (bf16, dropout applied) -> shared memory in the canonical K-major 128B-swizzled UMMA layout
+//             O = P V            (A = P K-major, B = V as an MN-major operand straight from its TMA tile)
+//   backward  S = Q K^T, dP = dO V^T                       (V's tile re-read as a K-major operand)
+//             dS = P (m dP - delta), delta_i = dO_i . O_i ;  Pd, dS -> shared memory once, as [i][j] bf16
+//             dV = Pd^T dO, dK = dS^T Q   (the same tiles read as MN-major A operands: no transposes)
+//             dQ = dS K
+// Q, K, V, dO tiles (128 rows x 64 head columns) arrive by TMA directly from the fused projection buffers
+// (row pitch = buffer width); rows past Nq / Nk belong to the next sample or are zero-filled and are neutralised
+// in the softmax (p = 0) — they never reach memory.  Semantics identical to attention.cu (reference
+// modules.py:190-199, :232-240): masked_fill(-1e9) after the bias add, fully padded rows are uniform.
+#include "tc_common.cuh"
+#include "../../include/mmnas_b200.h"
+
+namespace {
+
+constexpr int TILE_BYTES = 128 * 64 * 2;        // one 128 x 64 bf16 operand tile
+constexpr int PTILE_BYTES = 128 * 128 * 2;      // P / dS: two 64-wide k-chunks of 128 rows x 128 B
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct AttnTcArgs {
+  int B, heads, Nq, Nk;
+  const unsigned char* kmask;
+  const float* bias;
+  __nv_bfloat16* o; long ldo;
+  float scale;
+  DropCfg drop;
+  const __nv_bfloat16* dout; long lddo;
+  __nv_bfloat16 *dq, *dk, *dv; long lddq, lddk, lddv;
+  float* dbias;
+};
+
+// byte offset of element (row, col) in a [128 x 128] bf16 tile stored as two K-major SW128 chunks
+__device__ __forceinline__ uint32_t p_offset(int row, int col8) {   // col8 = column / 8 (16-byte granule index, 0..15)
+  const int kc = col8 >> 3, g = col8 & 7;
+  return (uint32_t)(kc * TILE_BYTES + row * 128 + ((g ^ (row & 7)) << 4));
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// logits of one 32-column chunk for row i: scale, bias, mask; columns >= Nk -> -inf
+__device__ __forceinline__ void chunk_logits(const AttnTcArgs& a, int b, int h, int i, bool row_ok, int j0, const uint32_t (&r)[32],
+                                             float (&s)[32]) {
+  const float* brow = (a.bias && row_ok) ? a.bias + (((size_t)b * a.heads + h) * a.Nq + i) * a.Nk : nullptr;
+  const unsigned char* mrow = a.kmask ? a.kmask + (size_t)b * a.Nk : nullptr;
+#pragma unroll
+  for (int t = 0; t < 32; ++t) {
+    const int j = j0 + t;
+    float v = -INFINITY;
+    if (j < a.Nk) {
+      v = __uint_as_float(r[t]) * a.scale;
+      if (brow) v += __ldg(brow + j);
+      if (mrow && mrow[j]) v = -1e9f;
+    }
+    s[t] = v;
+  }
+}
+
+__device__ __forceinline__ void tc_prologue(uint32_t bar_base, int nbars, uint32_t* tmem_slot, uint32_t cols, int warp) {
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < nbars; ++i) mbar_init(bar_base + 8u * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(128)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                   const __grid_constant__ CUtensorMap tv, AttnTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sQ = smem_u32(smem), sK = sQ + TILE_BYTES, sV = sK + TILE_BYTES, sP = sV + TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * TILE_BYTES + PTILE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const uint32_t bar = smem_u32(bars);
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int Nq = a.Nq, Nk = a.Nk;
+  tc_prologue(bar, 3, tmem_slot, 256, warp);
+  const uint32_t tmem = *tmem_slot;
+  const int n1 = max(16, (Nk + 15) & ~15);            // UMMA N of S = Q K^T
+  if (tid == 0) {
+    mbar_expect_tx(bar, 3 * TILE_BYTES);
+    tma_load_2d(sQ, &tq, bar, h * 64, b * Nq);
+    tma_load_2d(sK, &tk, bar, h * 64, b * Nk);
+    tma_load_2d(sV, &tv, bar, h * 64, b * Nk);
+    mbar_wait(bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t idesc = make_idesc(false, false, 128, n1);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+      umma_bf16(tmem, make_smem_desc(sQ + kk * 32, 16, 1024), make_smem_desc(sK + kk * 32, 16, 1024), idesc, kk > 0);
+    umma_commit(bar + 8);
+  }
+  mbar_wait(bar + 8, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  const int i = tid;
+  const bool row_ok = i < Nq;
+  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  const int NC = (Nk + 31) >> 5;
+  const bool use_drop = a.drop.state != nullptr && a.drop.thresh > 0;
+  const uint64_t key = use_drop ? drop_key(a.drop) : 0;
+  float mx = -INFINITY;
+  for (int cc = 0; cc < NC; ++cc) {
+    uint32_t r[32]; float s[32];
+    tmem_ld32(trow + cc * 32, r);
+    chunk_logits(a, b, h, i, row_ok, cc * 32, r, s);
+#pragma unroll
+    for (int t = 0; t < 32; ++t) mx = fmaxf(mx, s[t]);
+  }
+  float sum = 0.f;
+  for (int cc = 0; cc < NC; ++cc) {
+    uint32_t r[32]; float s[32];
+    tmem_ld32(trow + cc * 32, r);
+    chunk_logits(a, b, h, i, row_ok, cc * 32, r, s);
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+      float p = exp2f((s[t] - mx) * LOG2E);          // -inf -> 0
+      sum += p;
+      if (use_drop && row_ok && cc * 32 + t < Nk)
+        p *= drop_mult(key, (((uint64_t)b * a.heads + h) * Nq + i) * Nk + cc * 32 + t, a.drop.thresh, a.drop.scale);
+      s[t] = p;
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 pk = make_uint4(pack2(s[8 * g], s[8 * g + 1]), pack2(s[8 * g + 2], s[8 * g + 3]),
+                            pack2(s[8 * g + 4], s[8 * g + 5]), pack2(s[8 * g + 6], s[8 * g + 7]));
+      *reinterpret_cast<uint4*>(smem + 3 * TILE_BYTES + p_offset(i, cc * 4 + g)) = pk;
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy P writes -> visible to the MMA
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t idesc = make_idesc(false, true, 128, 64);
+    const int ksteps = (Nk + 15) >> 4;
+    for (int t = 0; t < ksteps; ++t)
+      umma_bf16(tmem + 128, make_smem_desc(sP + (t >> 2) * TILE_BYTES + (t & 3) * 32, 16, 1024),
+                make_smem_desc(sV + t * 2048, 8192, 1024), idesc, t > 0);
+    umma_commit(bar + 16);
+  }
+  mbar_wait(bar + 16, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const float inv = sum > 0.f ? 1.f / sum : 0.f;
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    uint32_t r[32];
+    tmem_ld32(trow + 128 + cc * 32, r);
+    if (row_ok) {
+      __nv_bfloat16* orow = a.o + ((size_t)b * Nq + i) * a.ldo + h * 64 + cc * 32;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 pk = make_uint4(pack2(__uint_as_float(r[8 * g]) * inv, __uint_as_float(r[8 * g + 1]) * inv),
+                              pack2(__uint_as_float(r[8 * g + 2]) * inv, __uint_as_float(r[8 * g + 3]) * inv),
+                              pack2(__uint_as_float(r[8 * g + 4]) * inv, __uint_as_float(r[8 * g + 5]) * inv),
+                              pack2(__uint_as_float(r[8 * g + 6]) * inv, __uint_as_float(r[8 * g + 7]) * inv));
+        *reinterpret_cast<uint4*>(orow + 8 * g) = pk;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+}
+
+__global__ void __launch_bounds__(128)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                   const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo, AttnTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sQ = smem_u32(smem), sK = sQ + TILE_BYTES, sV = sK + TILE_BYTES, sdO = sV + TILE_BYTES;
+  const uint32_t sP = sdO + TILE_BYTES, sdS = sP + PTILE_BYTES;
+  uint8_t* gP = smem + 4 * TILE_BYTES;
+  uint8_t* gdS = gP + PTILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 4 * TILE_BYTES + 2 * PTILE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const uint32_t bar = smem_u32(bars);
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int Nq = a.Nq, Nk = a.Nk;
+  tc_prologue(bar, 3, tmem_slot, 512, warp);
+  const uint32_t tmem = *tmem_slot;
+  // TMEM columns: S [0,128) dP [128,256) dQ [256,320) dK [320,384) dV [384,448)
+  const int n1 = max(16, (Nk + 15) & ~15);
+  if (tid == 0) {
+    mbar_expect_tx(bar, 4 * TILE_BYTES);
+    tma_load_2d(sQ, &tq, bar, h * 64, b * Nq);
+    tma_load_2d(sK, &tk, bar, h * 64, b * Nk);
+    tma_load_2d(sV, &tv, bar, h * 64, b * Nk);
+    tma_load_2d(sdO, &tdo, bar, h * 64, b * Nq);
+    mbar_wait(bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t idesc = make_idesc(false, false, 128, n1);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+      umma_bf16(tmem, make_smem_desc(sQ + kk * 32, 16, 1024), make_smem_desc(sK + kk * 32, 16, 1024), idesc, kk > 0);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)      // dP = dO V^T : V's tile as a K-major operand
+      umma_bf16(tmem + 128, make_smem_desc(sdO + kk * 32, 16, 1024), make_smem_desc(sV + kk * 32, 16, 1024), idesc, kk > 0);
+    umma_commit(bar + 8);
+  }
+  const int i = tid;
+  const bool row_ok = i < Nq;
+  // delta_i = dO_i . O_i from global while the MMAs run
+  float delta = 0.f;
+  if (row_ok) {
+    const uint4* orow = reinterpret_cast<const uint4*>(a.o + ((size_t)b * Nq + i) * a.ldo + h * 64);
+    const uint4* drow = reinterpret_cast<const uint4*>(a.dout + ((size_t)b * Nq + i) * a.lddo + h * 64);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const uint4 ov = __ldg(orow + g), dv = __ldg(drow + g);
+      const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov);
+      const __nv_bfloat162* d2 = reinterpret_cast<const __nv_bfloat162*>(&dv);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float2 of = __bfloat1622float2(o2[u]), df = __bfloat1622float2(d2[u]);
+        delta = fmaf(of.x, df.x, fmaf(of.y, df.y, delta));
+      }
+    }
+  }
+  mbar_wait(bar + 8, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  const int NC = (Nk + 31) >> 5;
+  const bool use_drop = a.drop.state != nullptr && a.drop.thresh > 0;
+  const uint64_t key = use_drop ? drop_key(a.drop) : 0;
+  float mx = -INFINITY;
+  for (int cc = 0; cc < NC; ++cc) {
+    uint32_t r[32]; float s[32];
+    tmem_ld32(trow + cc * 32, r);
+    chunk_logits(a, b, h, i, row_ok, cc * 32, r, s);
+#pragma unroll
+    for (int t = 0; t < 32; ++t) mx = fmaxf(mx, s[t]);
+  }
+  float sum = 0.f;
+  for (int cc = 0; cc < NC; ++cc) {
+    uint32_t r[32]; float s[32];
+    tmem_ld32(trow + cc * 32, r);
+    chunk_logits(a, b, h, i, row_ok, cc * 32, r, s);
+#pragma unroll
+    for (int t = 0; t < 32; ++t) sum += exp2f((s[t] - mx) * LOG2E);
+  }
+  const float inv = sum > 0.f ? 1.f / sum : 0.f;
+  const unsigned char* mrow = a.kmask ? a.kmask + (size_t)b * Nk : nullptr;
+  float* dbrow = (a.dbias && row_ok) ? a.dbias + (((size_t)b * a.heads + h) * Nq + i) * Nk : nullptr;
+  for (int cc = 0; cc < NC; ++cc) {
+    uint32_t r[32], rp[32]; float s[32], ds[32];
+    tmem_ld32(trow + cc * 32, r);
+    tmem_ld32(trow + 128 + cc * 32, rp);
+    chunk_logits(a, b, h, i, row_ok, cc * 32, r, s);
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+      const int j = cc * 32 + t;
+      float p = 0.f, d = 0.f;
+      if (row_ok && j < Nk) {
+        p = exp2f((s[t] - mx) * LOG2E) * inv;
+        float m = 1.f;
+        if (use_drop) m = drop_mult(key, (((uint64_t)b * a.heads + h) * Nq + i) * Nk + j, a.drop.thresh, a.drop.scale);
+        d = p * (m * __uint_as_float(rp[t]) - delta);
+        if (mrow && mrow[j]) d = 0.f;                 // masked_fill cuts the graph
+        p *= m;
+        if (dbrow) dbrow[j] = d;
+      }
+      s[t] = p; ds[t] = d;
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint32_t off = p_offset(i, cc * 4 + g);
+      *reinterpret_cast<uint4*>(gP + off) = make_uint4(pack2(s[8 * g], s[8 * g + 1]), pack2(s[8 * g + 2], s[8 * g + 3]),
+                                                       pack2(s[8 * g + 4], s[8 * g + 5]), pack2(s[8 * g + 6], s[8 * g + 7]));
+      *reinterpret_cast<uint4*>(gdS + off) = make_uint4(pack2(ds[8 * g], ds[8 * g + 1]), pack2(ds[8 * g + 2], ds[8 * g + 3]),
+                                                        pack2(ds[8 * g + 4], ds[8 * g + 5]), pack2(ds[8 * g + 6], ds[8 * g + 7]));
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int ksteps_j = (Nk + 15) >> 4, ksteps_i = (Nq + 15) >> 4;
+    // dQ = dS K : A = dS K-major (k = j), B = K tile as MN-major (k-rows j, n = head column)
+    const uint32_t id_q = make_idesc(false, true, 128, 64);
+    for (int t = 0; t < ksteps_j; ++t)
+      umma_bf16(tmem + 256, make_smem_desc(sdS + (t >> 2) * TILE_BYTES + (t & 3) * 32, 16, 1024),
+                make_smem_desc(sK + t * 2048, 8192, 1024), id_q, t > 0);
+    // dK = dS^T Q, dV = Pd^T dO : A = the same [i][j] tiles read MN-major (m = j: two 64-wide chunks, k-rows = i)
+    const uint32_t id_t = make_idesc(true, true, 128, 64);
+    for (int t = 0; t < ksteps_i; ++t)
+      umma_bf16(tmem + 320, make_smem_desc(sdS + t * 2048, TILE_BYTES, 1024), make_smem_desc(sQ + t * 2048, 8192, 1024), id_t, t > 0);
+    for (int t = 0; t < ksteps_i; ++t)
+      umma_bf16(tmem + 384, make_smem_desc(sP + t * 2048, TILE_BYTES, 1024), make_smem_desc(sdO + t * 2048, 8192, 1024), id_t, t > 0);
+    umma_commit(bar + 16);
+  }
+  mbar_wait(bar + 16, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // epilogue: thread t owns dQ row i = t and dK / dV row j = t
+#pragma unroll 1
+  for (int which = 0; which < 3; ++which) {
+    const bool ok = which == 0 ? row_ok : (tid < Nk);
+    const float mul = which == 2 ? 1.f : a.scale;
+    __nv_bfloat16* base = which == 0 ? a.dq + ((size_t)b * Nq + tid) * a.lddq
+                        : which == 1 ? a.dk + ((size_t)b * Nk + tid) * a.lddk
+                                     : a.dv + ((size_t)b * Nk + tid) * a.lddv;
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      uint32_t r[32];
+      tmem_ld32(trow + 256 + which * 64 + cc * 32, r);
+      if (ok) {
+        __nv_bfloat16* row = base + h * 64 + cc * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 pk = make_uint4(pack2(__uint_as_float(r[8 * g]) * mul, __uint_as_float(r[8 * g + 1]) * mul),
+                                pack2(__uint_as_float(r[8 * g + 2]) * mul, __uint_as_float(r[8 * g + 3]) * mul),
+                                pack2(__uint_as_float(r[8 * g + 4]) * mul, __uint_as_float(r[8 * g + 5]) * mul),
+                                pack2(__uint_as_float(r[8 * g + 6]) * mul, __uint_as_float(r[8 * g + 7]) * mul));
+          *reinterpret_cast<uint4*>(row + 8 * g) = pk;
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+constexpr int FWD_SMEM = 3 * TILE_BYTES + PTILE_BYTES + 1024 + 128;
+constexpr int BWD_SMEM = 4 * TILE_BYTES + 2 * PTILE_BYTES + 1024 + 128;
+
+DropCfg mk_drop(const unsigned long long* st, unsigned long long salt, float p) {
+  DropCfg d;
+  d.state = p > 0.f ? st : nullptr; d.salt = salt;
+  d.thresh = (unsigned)(p * 65536.f + 0.5f); d.scale = p < 1.f ? 1.f / (1.f - p) : 0.f;
+  return d;
+}
+
+bool aligned16(const void* p, long ld) { return ((uintptr_t)p % 16) == 0 && (ld % 8) == 0; }
+
+}  // namespace
+
+// Returns MMNAS_ERR_UNSUPPORTED when the operands do not meet the TMA constraints (caller then uses the FFMA kernel).
+int mmnas_attn_fwd_tc(int B, int heads, int Nq, int Nk, const void* q, long ldq, const void* k, long ldk, const void* v,
+                      long ldv, const unsigned char* kmask, const float* bias, void* o, long ldo, float scale,
+                      const unsigned long long* rng_state, unsigned long long salt, float p, cudaStream_t s) {
+  if (Nq > 128 || Nk > 128 || !aligned16(q, ldq) || !aligned16(k, ldk) || !aligned16(v, ldv) || !aligned16(o, ldo))
+    return MMNAS_ERR_UNSUPPORTED;
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = encode_2d(&tq, q, heads * 64, (long)B * Nq, ldq, 64, 128))) return rc;
+  if ((rc = encode_2d(&tk, k, heads * 64, (long)B * Nk, ldk, 64, 128))) return rc;
+  if ((rc = encode_2d(&tv, v, heads * 64, (long)B * Nk, ldv, 64, 128))) return rc;
+  AttnTcArgs a = {};
+  a.B = B; a.heads = heads; a.Nq = Nq; a.Nk = Nk; a.kmask = kmask; a.bias = bias;
+  a.o = (__nv_bfloat16*)o; a.ldo = ldo; a.scale = scale; a.drop = mk_drop(rng_state, salt, p);
+  static bool attr_done = false;
+  if (!attr_done) {
+    MMNAS_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    attr_done = true;
+  }
+  attn_fwd_tc_kernel<<<dim3(heads, B), 128, FWD_SMEM, s>>>(tq, tk, tv, a);
+  MMNAS_LAUNCH_CHECK();
+  return MMNAS_OK;
+}
+
+int mmnas_attn_bwd_tc(int B, int heads, int Nq, int Nk, const void* q, long ldq, const void* k, long ldk, const void* v,
+                      long ldv, const unsigned char* kmask, const float* bias, const void* o, long ldo, const void* dout,
+                      long lddo, void* dq, long lddq, void* dk, long lddk, void* dv, long lddv, float* dbias, float scale,
+                      const unsigned long long* rng_state, unsigned long long salt, float p, cudaStream_t s) {
+  if (Nq > 128 || Nk > 128 || !aligned16(q, ldq) || !aligned16(k, ldk) || !aligned16(v, ldv) || !aligned16(o, ldo) ||
+      !aligned16(dout, lddo) || !aligned16(dq, lddq) || !aligned16(dk, lddk) || !aligned16(dv, lddv))
+    return MMNAS_ERR_UNSUPPORTED;
+  CUtensorMap tq, tk, tv, tdo;
+  int rc;
+  if ((rc = encode_2d(&tq, q, heads * 64, (long)B * Nq, ldq, 64, 128))) return rc;
+  if ((rc = encode_2d(&tk, k, heads * 64, (long)B * Nk, ldk, 64, 128))) return rc;
+  if ((rc = encode_2d(&tv, v, heads * 64, (long)B * Nk, ldv, 64, 128))) return rc;
+  if ((rc = encode_2d(&tdo, dout, heads * 64, (long)B * Nq, lddo, 64, 128))) return rc;
+  AttnTcArgs a = {};
+  a.B = B; a.heads = heads; a.Nq = Nq; a.Nk = Nk; a.kmask = kmask; a.bias = bias;
+  a.o = (__nv_bfloat16*)const_cast<void*>(o); a.ldo = ldo; a.scale = scale; a.drop = mk_drop(rng_state, salt, p);
+  a.dout = (const __nv_bfloat16*)dout; a.lddo = lddo;
+  a.dq = (__nv_bfloat16*)dq; a.dk = (__nv_bfloat16*)dk; a.dv = (__nv_bfloat16*)dv;
+  a.lddq = lddq; a.lddk = lddk; a.lddv = lddv; a.dbias = dbias;
+  static bool attr_done = false;
+  if (!attr_done) {
+    MMNAS_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    attr_done = true;
+  }
+  attn_bwd_tc_kernel<<<dim3(heads, B), 128, BWD_SMEM, s>>>(tq, tk, tv, tdo, a);
+  MMNAS_LAUNCH_CHECK();
+  return MMNAS_OK;
+}
