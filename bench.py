@@ -231,7 +231,7 @@ def run_b200(args):
     host_batches = [make_batch(spec, seed=1000 + 17 * rank + i) for i in range(2)]
     inputs, target = host_batches[0]
     dev_in, dev_tgt = tuple(t.to(dev) for t in inputs), target.to(dev)
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = not args.no_graph and (world == 1 or os.environ.get('MMNAS_DP_GRAPH', '0') == '1')
     step = TrainStep(net, lr_base=cfg.NET_LR_BASE, epoch_steps=10 ** 6, use_graph=use_graph)
 
     def barrier():

@@ -31,6 +31,7 @@ SIGNATURES = {
     'mmnas_mixed_accum': [c_i, c_p, c_p, c_p, c_l, c_p],
     'mmnas_mixed_alpha_dot': [c_i, c_p, c_p, c_p, c_p, c_p, c_l, c_p],
     'mmnas_cast_f32_to_bf16': [c_p, c_p, c_l, c_p],
+    'mmnas_cast_multi': [c_p, c_i, c_p],
     'mmnas_colsum': [c_i, c_p, c_i, c_i, c_l, c_p, c_p],
     'mmnas_rng_advance': [c_p, c_p],
 }

@@ -44,21 +44,67 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-// logits of one 32-column chunk for row i: scale, bias, mask; columns >= Nk -> -inf
-__device__ __forceinline__ void chunk_logits(const AttnTcArgs& a, int b, int h, int i, bool row_ok, int j0, const uint32_t (&r)[32],
-                                             float (&s)[32]) {
-  const float* brow = (a.bias && row_ok) ? a.bias + (((size_t)b * a.heads + h) * a.Nq + i) * a.Nk : nullptr;
+// Row-resident softmax state of one thread (= one query row = one TMEM lane): up to 4 chunks of 32 logits.
+struct RowCtx {
+  uint32_t mk[4];          // padded-key bitmask, bit t of word c = key 32c+t (warp-uniform)
+  const float* brow;       // bias row or null
+  bool vec;                // bias / dbias rows are 16-byte aligned (Nk % 4 == 0)
+  uint64_t rowbase;        // dropout element index of (row, key 0)
+};
+
+__device__ __forceinline__ RowCtx make_row_ctx(const AttnTcArgs& a, int b, int h, int i, bool row_ok, int lane) {
+  RowCtx c;
   const unsigned char* mrow = a.kmask ? a.kmask + (size_t)b * a.Nk : nullptr;
 #pragma unroll
-  for (int t = 0; t < 32; ++t) {
-    const int j = j0 + t;
-    float v = -INFINITY;
-    if (j < a.Nk) {
-      v = __uint_as_float(r[t]) * a.scale;
-      if (brow) v += __ldg(brow + j);
-      if (mrow && mrow[j]) v = -1e9f;
+  for (int w = 0; w < 4; ++w) {
+    const int j = w * 32 + lane;
+    const bool m = mrow != nullptr && j < a.Nk && mrow[j] != 0;
+    c.mk[w] = __ballot_sync(0xffffffffu, m);
+  }
+  c.rowbase = (((uint64_t)b * a.heads + h) * a.Nq + i) * a.Nk;
+  c.brow = (a.bias && row_ok) ? a.bias + c.rowbase : nullptr;
+  c.vec = (a.Nk & 3) == 0;
+  return c;
+}
+
+// logits of chunk cc from the raw accumulator: scale, bias, mask; keys >= Nk -> -inf
+__device__ __forceinline__ void chunk_logits(const AttnTcArgs& a, const RowCtx& c, int cc, const uint32_t (&r)[32], float (&s)[32]) {
+  const int j0 = cc * 32;
+  float bb[32];
+#pragma unroll
+  for (int t = 0; t < 32; ++t) bb[t] = 0.f;
+  if (c.brow) {
+    if (c.vec) {
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        if (j0 + 4 * g < a.Nk) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(c.brow + j0) + g);
+          bb[4 * g] = v.x; bb[4 * g + 1] = v.y; bb[4 * g + 2] = v.z; bb[4 * g + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 32; ++t)
+        if (j0 + t < a.Nk) bb[t] = __ldg(c.brow + j0 + t);
     }
-    s[t] = v;
+  }
+  const uint32_t mk = c.mk[cc];
+#pragma unroll
+  for (int t = 0; t < 32; ++t) {
+    float v = fmaf(__uint_as_float(r[t]), a.scale, bb[t]);
+    if ((mk >> t) & 1u) v = -1e9f;
+    s[t] = (j0 + t < a.Nk) ? v : -INFINITY;
+  }
+}
+
+// dropout multipliers of 4 consecutive keys j..j+3 (j % 4 == 0) of this row: one hash when the row is 4-aligned
+__device__ __forceinline__ void drop4(const AttnTcArgs& a, const RowCtx& c, uint64_t key, int j, float (&m)[4]) {
+  if (c.vec) {
+    const uint64_t r = mmnas_mix64(key ^ (((c.rowbase + j) >> 2) * 0x9E3779B97F4A7C15ull));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) m[u] = ((unsigned)(r >> (16 * u)) & 0xFFFFu) < a.drop.thresh ? 0.f : a.drop.scale;
+  } else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) m[u] = drop_mult(key, c.rowbase + j + u, a.drop.thresh, a.drop.scale);
   }
 }
 
@@ -76,7 +122,7 @@ __device__ __forceinline__ void tc_prologue(uint32_t bar_base, int nbars, uint32
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                    const __grid_constant__ CUtensorMap tv, AttnTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -113,34 +159,46 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   const int NC = (Nk + 31) >> 5;
   const bool use_drop = a.drop.state != nullptr && a.drop.thresh > 0;
   const uint64_t key = use_drop ? drop_key(a.drop) : 0;
+  const RowCtx ctx = make_row_ctx(a, b, h, i, row_ok, tid & 31);
+  float s[4][32];                                   // the whole row stays in registers: TMEM is read once
   float mx = -INFINITY;
-  for (int cc = 0; cc < NC; ++cc) {
-    uint32_t r[32]; float s[32];
-    tmem_ld32(trow + cc * 32, r);
-    chunk_logits(a, b, h, i, row_ok, cc * 32, r, s);
 #pragma unroll
-    for (int t = 0; t < 32; ++t) mx = fmaxf(mx, s[t]);
-  }
+  for (int cc = 0; cc < 4; ++cc)
+    if (cc < NC) {
+      uint32_t r[32];
+      tmem_ld32(trow + cc * 32, r);
+      chunk_logits(a, ctx, cc, r, s[cc]);
+#pragma unroll
+      for (int t = 0; t < 32; ++t) mx = fmaxf(mx, s[cc][t]);
+    }
   float sum = 0.f;
-  for (int cc = 0; cc < NC; ++cc) {
-    uint32_t r[32]; float s[32];
-    tmem_ld32(trow + cc * 32, r);
-    chunk_logits(a, b, h, i, row_ok, cc * 32, r, s);
+  const float mxl = mx * LOG2E;
 #pragma unroll
-    for (int t = 0; t < 32; ++t) {
-      float p = exp2f((s[t] - mx) * LOG2E);          // -inf -> 0
-      sum += p;
-      if (use_drop && row_ok && cc * 32 + t < Nk)
-        p *= drop_mult(key, (((uint64_t)b * a.heads + h) * Nq + i) * Nk + cc * 32 + t, a.drop.thresh, a.drop.scale);
-      s[t] = p;
-    }
+  for (int cc = 0; cc < 4; ++cc)
+    if (cc < NC) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      uint4 pk = make_uint4(pack2(s[8 * g], s[8 * g + 1]), pack2(s[8 * g + 2], s[8 * g + 3]),
-                            pack2(s[8 * g + 4], s[8 * g + 5]), pack2(s[8 * g + 6], s[8 * g + 7]));
-      *reinterpret_cast<uint4*>(smem + 3 * TILE_BYTES + p_offset(i, cc * 4 + g)) = pk;
+      for (int t = 0; t < 32; ++t) {
+        const float p = exp2f(fmaf(s[cc][t], LOG2E, -mxl));      // -inf -> 0
+        sum += p;
+        s[cc][t] = p;
+      }
+      if (use_drop && row_ok) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          if (cc * 32 + 4 * g < Nk) {
+            float m[4];
+            drop4(a, ctx, key, cc * 32 + 4 * g, m);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) s[cc][4 * g + u] *= m[u];
+          }
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 pk = make_uint4(pack2(s[cc][8 * g], s[cc][8 * g + 1]), pack2(s[cc][8 * g + 2], s[cc][8 * g + 3]),
+                              pack2(s[cc][8 * g + 4], s[cc][8 * g + 5]), pack2(s[cc][8 * g + 6], s[cc][8 * g + 7]));
+        *reinterpret_cast<uint4*>(smem + 3 * TILE_BYTES + p_offset(i, cc * 4 + g)) = pk;
+      }
     }
-  }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy P writes -> visible to the MMA
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -177,7 +235,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                    const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo, AttnTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -238,54 +296,70 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   const int NC = (Nk + 31) >> 5;
   const bool use_drop = a.drop.state != nullptr && a.drop.thresh > 0;
   const uint64_t key = use_drop ? drop_key(a.drop) : 0;
+  const RowCtx ctx = make_row_ctx(a, b, h, i, row_ok, tid & 31);
+  float s[4][32];
   float mx = -INFINITY;
-  for (int cc = 0; cc < NC; ++cc) {
-    uint32_t r[32]; float s[32];
-    tmem_ld32(trow + cc * 32, r);
-    chunk_logits(a, b, h, i, row_ok, cc * 32, r, s);
 #pragma unroll
-    for (int t = 0; t < 32; ++t) mx = fmaxf(mx, s[t]);
-  }
+  for (int cc = 0; cc < 4; ++cc)
+    if (cc < NC) {
+      uint32_t r[32];
+      tmem_ld32(trow + cc * 32, r);
+      chunk_logits(a, ctx, cc, r, s[cc]);
+#pragma unroll
+      for (int t = 0; t < 32; ++t) mx = fmaxf(mx, s[cc][t]);
+    }
   float sum = 0.f;
-  for (int cc = 0; cc < NC; ++cc) {
-    uint32_t r[32]; float s[32];
-    tmem_ld32(trow + cc * 32, r);
-    chunk_logits(a, b, h, i, row_ok, cc * 32, r, s);
+  const float mxl = mx * LOG2E;
 #pragma unroll
-    for (int t = 0; t < 32; ++t) sum += exp2f((s[t] - mx) * LOG2E);
-  }
-  const float inv = sum > 0.f ? 1.f / sum : 0.f;
-  const unsigned char* mrow = a.kmask ? a.kmask + (size_t)b * Nk : nullptr;
-  float* dbrow = (a.dbias && row_ok) ? a.dbias + (((size_t)b * a.heads + h) * Nq + i) * Nk : nullptr;
-  for (int cc = 0; cc < NC; ++cc) {
-    uint32_t r[32], rp[32]; float s[32], ds[32];
-    tmem_ld32(trow + cc * 32, r);
-    tmem_ld32(trow + 128 + cc * 32, rp);
-    chunk_logits(a, b, h, i, row_ok, cc * 32, r, s);
+  for (int cc = 0; cc < 4; ++cc)
+    if (cc < NC) {
 #pragma unroll
-    for (int t = 0; t < 32; ++t) {
-      const int j = cc * 32 + t;
-      float p = 0.f, d = 0.f;
-      if (row_ok && j < Nk) {
-        p = exp2f((s[t] - mx) * LOG2E) * inv;
-        float m = 1.f;
-        if (use_drop) m = drop_mult(key, (((uint64_t)b * a.heads + h) * Nq + i) * Nk + j, a.drop.thresh, a.drop.scale);
-        d = p * (m * __uint_as_float(rp[t]) - delta);
-        if (mrow && mrow[j]) d = 0.f;                 // masked_fill cuts the graph
-        p *= m;
-        if (dbrow) dbrow[j] = d;
+      for (int t = 0; t < 32; ++t) {
+        s[cc][t] = exp2f(fmaf(s[cc][t], LOG2E, -mxl));
+        sum += s[cc][t];
       }
-      s[t] = p; ds[t] = d;
     }
+  const float inv = (row_ok && sum > 0.f) ? 1.f / sum : 0.f;     // rows >= Nq contribute zeros to dK / dV
+  float* dbrow = (a.dbias && row_ok) ? a.dbias + ctx.rowbase : nullptr;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const uint32_t off = p_offset(i, cc * 4 + g);
-      *reinterpret_cast<uint4*>(gP + off) = make_uint4(pack2(s[8 * g], s[8 * g + 1]), pack2(s[8 * g + 2], s[8 * g + 3]),
-                                                       pack2(s[8 * g + 4], s[8 * g + 5]), pack2(s[8 * g + 6], s[8 * g + 7]));
-      *reinterpret_cast<uint4*>(gdS + off) = make_uint4(pack2(ds[8 * g], ds[8 * g + 1]), pack2(ds[8 * g + 2], ds[8 * g + 3]),
-                                                        pack2(ds[8 * g + 4], ds[8 * g + 5]), pack2(ds[8 * g + 6], ds[8 * g + 7]));
+  for (int cc = 0; cc < 4; ++cc)
+    if (cc < NC) {
+      uint32_t rp[32];
+      float ds[32];
+      tmem_ld32(trow + 128 + cc * 32, rp);
+      const uint32_t mk = ctx.mk[cc];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        float m[4] = {1.f, 1.f, 1.f, 1.f};
+        if (use_drop && cc * 32 + 4 * g < Nk) drop4(a, ctx, key, cc * 32 + 4 * g, m);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int t = 4 * g + u;
+          const float p = s[cc][t] * inv;                          // 0 for keys >= Nk (exp2(-inf)) and rows >= Nq
+          float d = p * (m[u] * __uint_as_float(rp[t]) - delta);
+          if (((mk >> t) & 1u) || p == 0.f) d = 0.f;               // masked_fill cuts the graph; p == 0 guards garbage dP
+          s[cc][t] = p * m[u];
+          ds[t] = d;
+        }
+        if (dbrow && cc * 32 + 4 * g < Nk) {
+          if (ctx.vec) {
+            *reinterpret_cast<float4*>(dbrow + cc * 32 + 4 * g) = make_float4(ds[4 * g], ds[4 * g + 1], ds[4 * g + 2], ds[4 * g + 3]);
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (cc * 32 + 4 * g + u < Nk) dbrow[cc * 32 + 4 * g + u] = ds[4 * g + u];
+          }
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint32_t off = p_offset(i, cc * 4 + g);
+        *reinterpret_cast<uint4*>(gP + off) = make_uint4(pack2(s[cc][8 * g], s[cc][8 * g + 1]), pack2(s[cc][8 * g + 2], s[cc][8 * g + 3]),
+                                                         pack2(s[cc][8 * g + 4], s[cc][8 * g + 5]), pack2(s[cc][8 * g + 6], s[cc][8 * g + 7]));
+        *reinterpret_cast<uint4*>(gdS + off) = make_uint4(pack2(ds[8 * g], ds[8 * g + 1]), pack2(ds[8 * g + 2], ds[8 * g + 3]),
+                                                          pack2(ds[8 * g + 4], ds[8 * g + 5]), pack2(ds[8 * g + 6], ds[8 * g + 7]));
+      }
     }
-  }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();

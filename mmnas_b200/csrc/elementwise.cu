@@ -113,6 +113,22 @@ __global__ void __launch_bounds__(EW_THREADS) mixed_alpha_dot_kernel(MixedArgs a
   }
 }
 
+// One launch casts every weight of the model: table[c] = {src pointer, dst pointer, element count (<= 4096, % 4 == 0)}
+__global__ void __launch_bounds__(EW_THREADS) cast_multi_kernel(const long long* __restrict__ table) {
+  const long long* e = table + 3 * (long long)blockIdx.x;
+  const float* src = reinterpret_cast<const float*>(e[0]);
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e[1]);
+  const int nvec = (int)(e[2] >> 2);
+  for (int v = threadIdx.x; v < nvec; v += EW_THREADS) {
+    const float4 f = *reinterpret_cast<const float4*>(src + 4 * v);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(f.x, f.y), hi = __floats2bfloat162_rn(f.z, f.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<unsigned*>(&lo);
+    pk.y = *reinterpret_cast<unsigned*>(&hi);
+    *reinterpret_cast<uint2*>(dst + 4 * v) = pk;
+  }
+}
+
 __global__ void rng_advance_kernel(unsigned long long* state) { state[1] += 1ull; }
 
 }  // namespace
@@ -123,6 +139,15 @@ extern "C" int mmnas_cast_f32_to_bf16(const float* src, void* dst, long n, mmnas
   MMNAS_CHECK_ARG(src && dst, "cast: null buffer");
   MMNAS_CHECK_ARG(((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 8) == 0, "cast: buffers must be 16-byte aligned");
   cast_kernel<<<ew_grid(n >> 2), EW_THREADS, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+  MMNAS_LAUNCH_CHECK();
+  return MMNAS_OK;
+}
+
+extern "C" int mmnas_cast_multi(const void* table, int n_chunks, mmnas_stream stream) {
+  MMNAS_CHECK_ARG(n_chunks >= 0, "cast_multi: negative chunk count");
+  if (n_chunks == 0) return MMNAS_OK;
+  MMNAS_CHECK_ARG(table, "cast_multi: null table");
+  cast_multi_kernel<<<n_chunks, EW_THREADS, 0, (cudaStream_t)stream>>>((const long long*)table);
   MMNAS_LAUNCH_CHECK();
   return MMNAS_OK;
 }

@@ -16,6 +16,7 @@
 //   (+bias, ReLU, dropout with one hash per 4 elements, ReLU-mask of a saved activation, fp32 accumulate,
 //   bf16/fp32 store, split-K red.add.v4) happens in that coalesced layout.
 //   BN = 256 (single 128x256x16 UMMA, half the operand traffic per FLOP) when it does not cost a wave.
+#include <cstdlib>
 #include "tc_common.cuh"
 #include "../../include/mmnas_b200.h"
 
@@ -52,11 +53,9 @@ __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
 }
 
 // epilogue math on 4 consecutive columns of one row, then the store — all accesses row-contiguous
-__device__ __forceinline__ void epilogue_store4(const TcEpilogue& ep, float4 v, int row, int col, bool add_bias, uint64_t key) {
-  if (add_bias) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
-    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-  }
+__device__ __forceinline__ void epilogue_store4(const TcEpilogue& ep, float4 v, int row, int col, const float4& b, uint64_t key,
+                                                const float4& old, const uint2& auxpk) {
+  v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
   if (ep.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
   if (ep.use_drop) {      // same stream as drop_mult(): one 64-bit hash per group of 4 elements
     const uint64_t idx = (uint64_t)row * ep.N + col;
@@ -67,7 +66,7 @@ __device__ __forceinline__ void epilogue_store4(const TcEpilogue& ep, float4 v, 
     v.w *= ((unsigned)(r >> 48) & 0xFFFFu) < ep.drop.thresh ? 0.f : ep.drop.scale;
   }
   if (ep.aux) {
-    const uint2 pk = __ldg(reinterpret_cast<const uint2*>(ep.aux + (long)row * ep.ld_aux + col));
+    const uint2 pk = auxpk;
     const __nv_bfloat162 a01 = *reinterpret_cast<const __nv_bfloat162*>(&pk.x);
     const __nv_bfloat162 a23 = *reinterpret_cast<const __nv_bfloat162*>(&pk.y);
     v.x = __low2float(a01) > 0.f ? v.x * ep.aux_scale : 0.f;
@@ -86,10 +85,7 @@ __device__ __forceinline__ void epilogue_store4(const TcEpilogue& ep, float4 v, 
     if (ep.split_k > 1) {
       red_add_v4(cp, v);
     } else {
-      if (ep.accumulate) {
-        const float4 old = *reinterpret_cast<const float4*>(cp);
-        v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
-      }
+      v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;    // zeros unless ep.accumulate
       *reinterpret_cast<float4*>(cp) = v;
     }
   }
@@ -222,12 +218,29 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int g = 0; g < 8; ++g)
           *reinterpret_cast<uint4*>(stg + lane * STG_PITCH + 4 * g) = make_uint4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
         __syncwarp();
+        // all global reads of the chunk (old C for accumulate, the ReLU-mask activation, bias) are issued before
+        // any dependent math, so their latencies overlap instead of serialising 8 load->add->store chains
+        const int col = col0 + col4;
+        float4 bia = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (add_bias) bia = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+        float4 old[8];
+        uint2 auxpk[8];
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr) {
+          const int row = row_base + itr * 4 + sub_r;
+          old[itr] = make_float4(0.f, 0.f, 0.f, 0.f);
+          auxpk[itr] = make_uint2(0u, 0u);
+          if (row < ep.M) {
+            if (ep.accumulate) old[itr] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.C) + (long)row * ep.ldc + col);
+            if (ep.aux) auxpk[itr] = __ldg(reinterpret_cast<const uint2*>(ep.aux + (long)row * ep.ld_aux + col));
+          }
+        }
 #pragma unroll
         for (int itr = 0; itr < 8; ++itr) {
           const int rr = itr * 4 + sub_r;
           const int row = row_base + rr;
           const float4 v = *reinterpret_cast<const float4*>(stg + rr * STG_PITCH + col4);
-          if (row < ep.M) epilogue_store4(ep, v, row, col0 + col4, add_bias, key);
+          if (row < ep.M) epilogue_store4(ep, v, row, col, bia, key, old[itr], auxpk[itr]);
         }
         __syncwarp();
       }
@@ -306,6 +319,10 @@ extern "C" int mmnas_gemm_bf16(int M, int N, int K, const void* A, long lda, int
     const int w128 = ceil_div(tiles_m * ceil_div(N, 128), sms);
     const int w256 = 2 * ceil_div(tiles_m * ceil_div(N, 256), sms);
     if (w256 <= w128) bn = 256;
+  }
+  if (const char* e = getenv("MMNAS_GEMM_BN")) {        // tuning / A-B experiments only
+    const int forced = atoi(e);
+    if (forced == 128 || (forced == 256 && split_k == 1 && N % 256 == 0)) bn = forced;
   }
   CUtensorMap ta, tb;
   int rc;

@@ -102,6 +102,10 @@ def cast_bf16(src, dst=None):
     return dst
 
 
+def cast_multi(table, n_chunks):
+    call('mmnas_cast_multi', ptr(table), n_chunks, stream())
+
+
 def colsum(x, rows, cols, ld, out):
     call('mmnas_colsum', _code(x), ptr(x), rows, cols, ld, ptr(out), stream())
 

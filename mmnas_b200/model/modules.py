@@ -75,8 +75,12 @@ class _OpBase(nn.Module):
     def _fused_bf16(self, name, params):
         """bf16 copy of `params` stacked along dim 0.  Re-cast on every training forward (the optimizer step may
         sit inside a captured CUDA graph, where version counters do not move); version-checked in eval."""
-        vers = tuple((p.data_ptr(), p._version) for p in params)
         ent = self._w16.get(name)
+        if ent is not None and ent[0] == 'managed' and runtime.shadows_fresh:
+            return ent[1]            # refreshed by engine.WeightShadows in one batched cast this step
+        if ent is not None and ent[0] == 'managed':
+            ent = (None, ent[1])     # outside an engine step: cast here, into the same buffer
+        vers = tuple((p.data_ptr(), p._version) for p in params)
         live = self.training
         if ent is not None and not live and ent[0] == vers and ent[1].device == params[0].device:
             return ent[1]
@@ -88,7 +92,8 @@ class _OpBase(nn.Module):
         for p in params:
             K.cast_bf16(p.detach(), buf[r:r + p.shape[0]])
             r += p.shape[0]
-        self._w16[name] = (vers, buf)
+        if self._w16.get(name, (None,))[0] != 'managed':
+            self._w16[name] = (vers, buf)
         return buf
 
 
@@ -239,6 +244,17 @@ class _AttOp(nn.Module):
         if norm:
             self.ln = LayerNorm(__C.HSIZE)
 
+    GUIDED = False
+
+    def shadow_specs(self):
+        """(owner module, shadow name, [weights stacked along dim 0]) for engine.WeightShadows."""
+        m = self.mhatt
+        if self.GUIDED:
+            specs = [(m, 'q', [m.linear_q.weight]), (m, 'kv', [m.linear_k.weight, m.linear_v.weight])]
+        else:
+            specs = [(m, 'qkv', [m.linear_q.weight, m.linear_k.weight, m.linear_v.weight])]
+        return specs + [(m, 'm', [m.linear_merge.weight])]
+
     def _run(self, x, kv, mask, rel_embed):
         return self.mhatt.run_block(x, kv, mask, rel_embed, self.ln if self.norm else None, self.residual,
                                     self.DROPOUT_R)
@@ -258,6 +274,8 @@ class RelSelfAtt(_AttOp):
 
 
 class GuidedAtt(_AttOp):
+    GUIDED = True
+
     def forward(self, x, y=None, x_mask=None, y_mask=None, rel_embed=None):
         assert y is not None
         return self._run(x, y, y_mask, None)
@@ -275,6 +293,9 @@ class FeedForward(_OpBase):
         if norm:
             self.ln = LayerNorm(__C.HSIZE)
         self._init_runtime(2)     # sites: hidden activation, block output
+
+    def shadow_specs(self):
+        return [(self, 'w1', [self.mlp.fc.linear.weight]), (self, 'w2', [self.mlp.linear.weight])]
 
     def forward(self, x, y=None, x_mask=None, y_mask=None, rel_embed=None):
         require_cuda(x)

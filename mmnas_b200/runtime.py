@@ -8,6 +8,7 @@ from . import kernels
 
 _PRECISION = 'bf16'          # 'fp32' (FFMA kernels, 1e-5 parity arm) | 'bf16' (tcgen05 arm, 2e-2)
 _rng_states = {}
+shadows_fresh = False      # True while an engine step guarantees that the managed bf16 weight shadows are current
 _salt_counter = itertools.count(1)
 _lock = threading.Lock()
 

