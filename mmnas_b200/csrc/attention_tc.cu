@@ -135,6 +135,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   const int tid = threadIdx.x, warp = tid >> 5;
   const int Nq = a.Nq, Nk = a.Nk;
   tc_prologue(bar, 3, tmem_slot, 256, warp);
+  pdl_wait();                       // prologue above overlapped the previous kernel's tail
   const uint32_t tmem = *tmem_slot;
   const int n1 = max(16, (Nk + 15) & ~15);            // UMMA N of S = Q K^T
   if (tid == 0) {
@@ -213,6 +214,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   }
   mbar_wait(bar + 16, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  pdl_launch();
   const float inv = sum > 0.f ? 1.f / sum : 0.f;
 #pragma unroll
   for (int cc = 0; cc < 2; ++cc) {
@@ -251,6 +253,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   const int tid = threadIdx.x, warp = tid >> 5;
   const int Nq = a.Nq, Nk = a.Nk;
   tc_prologue(bar, 3, tmem_slot, 512, warp);
+  pdl_wait();
   const uint32_t tmem = *tmem_slot;
   // TMEM columns: S [0,128) dP [128,256) dQ [256,320) dK [320,384) dV [384,448)
   const int n1 = max(16, (Nk + 15) & ~15);
@@ -381,6 +384,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   }
   mbar_wait(bar + 16, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  pdl_launch();
   // epilogue: thread t owns dQ row i = t and dK / dV row j = t
 #pragma unroll 1
   for (int which = 0; which < 3; ++which) {
@@ -444,8 +448,7 @@ int mmnas_attn_fwd_tc(int B, int heads, int Nq, int Nk, const void* q, long ldq,
     MMNAS_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
     attr_done = true;
   }
-  attn_fwd_tc_kernel<<<dim3(heads, B), 128, FWD_SMEM, s>>>(tq, tk, tv, a);
-  MMNAS_LAUNCH_CHECK();
+  MMNAS_CUDA(mmnas_launch(attn_fwd_tc_kernel, dim3(heads, B), dim3(128), FWD_SMEM, s, tq, tk, tv, a));
   return MMNAS_OK;
 }
 
@@ -473,7 +476,6 @@ int mmnas_attn_bwd_tc(int B, int heads, int Nq, int Nk, const void* q, long ldq,
     MMNAS_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
     attr_done = true;
   }
-  attn_bwd_tc_kernel<<<dim3(heads, B), 128, BWD_SMEM, s>>>(tq, tk, tv, tdo, a);
-  MMNAS_LAUNCH_CHECK();
+  MMNAS_CUDA(mmnas_launch(attn_bwd_tc_kernel, dim3(heads, B), dim3(128), BWD_SMEM, s, tq, tk, tv, tdo, a));
   return MMNAS_OK;
 }

@@ -2,6 +2,7 @@
 // column sums (bias gradients), the supernet mixed-op accumulate and its alpha-gate gradient
 // (mixed.py:60-68 and the autograd rule SURVEY §8 a11), and the dropout step counter.
 // All are vectorised (float4 / 8-byte bf16x4), grid-stride, grid = k x 148 SMs.
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/mmnas_b200.h"
 
@@ -15,6 +16,7 @@ inline int ew_grid(long nvec) {
 }
 
 __global__ void __launch_bounds__(EW_THREADS) cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long n) {
+  pdl_wait(); pdl_launch();
   const long nvec = n >> 2;
   for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (long)gridDim.x * blockDim.x) {
     float4 f = *reinterpret_cast<const float4*>(src + 4 * v);
@@ -30,21 +32,45 @@ __global__ void __launch_bounds__(EW_THREADS) cast_kernel(const float* __restric
   }
 }
 
-// out[c] = sum_r x[r, c];  CTA (32 x 8) owns 32 columns and a slab of rows; smem combine; atomics.
+// out[c] = sum_r x[r, c].  A thread owns 8 consecutive columns (one 16-byte bf16 load / two float4 loads per row),
+// a CTA = 32 column groups x 8 row lanes over a slab of rows; smem combine; one atomic per column per CTA.
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, int rows, int cols, long ld, float* __restrict__ out) {
-  __shared__ float red[8][33];
+  __shared__ float red[8][32 * 8 + 8];
+  pdl_wait(); pdl_launch();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + tx;
-  float s = 0.f;
-  if (c < cols)
-    for (int r = blockIdx.y * 8 + ty; r < rows; r += gridDim.y * 8) s += to_f32<T>(x[(long)r * ld + c]);
-  red[ty][tx] = s;
+  const int c0 = (blockIdx.x * 32 + tx) * 8;
+  float s[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) s[u] = 0.f;
+  const bool vec = (c0 + 8 <= cols) && (ld % 8 == 0);
+  if (c0 < cols)
+    for (int r = blockIdx.y * 8 + ty; r < rows; r += gridDim.y * 8) {
+      const T* p = x + (long)r * ld + c0;
+      if (vec) {
+        if (sizeof(T) == 2) {
+          const uint4 v = *reinterpret_cast<const uint4*>(p);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { const float2 f = __bfloat1622float2(h[u]); s[2 * u] += f.x; s[2 * u + 1] += f.y; }
+        } else {
+          const float4 a = *reinterpret_cast<const float4*>(p), b = *(reinterpret_cast<const float4*>(p) + 1);
+          s[0] += a.x; s[1] += a.y; s[2] += a.z; s[3] += a.w; s[4] += b.x; s[5] += b.y; s[6] += b.z; s[7] += b.w;
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (c0 + u < cols) s[u] += to_f32<T>(p[u]);
+      }
+    }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) red[ty][tx * 8 + u] = s[u];
   __syncthreads();
-  if (ty == 0 && c < cols) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < cols) {
     float tot = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) tot += red[k][tx];
+    for (int k = 0; k < 8; ++k) tot += red[k][threadIdx.x];
     atomicAdd(&out[c], tot);
   }
 }
@@ -62,6 +88,7 @@ struct MixedArgs {
 };
 
 __global__ void __launch_bounds__(EW_THREADS) mixed_accum_kernel(MixedArgs a) {
+  pdl_wait(); pdl_launch();
   float g[MAXK];
 #pragma unroll
   for (int k = 0; k < MAXK; ++k) g[k] = k < a.K ? a.gate[k] : 0.f;
@@ -82,6 +109,7 @@ __global__ void __launch_bounds__(EW_THREADS) mixed_accum_kernel(MixedArgs a) {
 // gate_grad[k] = <o_k, dout>;  d_o[k] = gate[k] * dout for the candidates that take gradient.
 __global__ void __launch_bounds__(EW_THREADS) mixed_alpha_dot_kernel(MixedArgs a) {
   __shared__ float red[MAXK][EW_THREADS / 32];
+  pdl_wait(); pdl_launch();
   float g[MAXK], dot[MAXK];
 #pragma unroll
   for (int k = 0; k < MAXK; ++k) { g[k] = k < a.K ? a.gate[k] : 0.f; dot[k] = 0.f; }
@@ -115,6 +143,7 @@ __global__ void __launch_bounds__(EW_THREADS) mixed_alpha_dot_kernel(MixedArgs a
 
 // One launch casts every weight of the model: table[c] = {src pointer, dst pointer, element count (<= 4096, % 4 == 0)}
 __global__ void __launch_bounds__(EW_THREADS) cast_multi_kernel(const long long* __restrict__ table) {
+  pdl_wait(); pdl_launch();
   const long long* e = table + 3 * (long long)blockIdx.x;
   const float* src = reinterpret_cast<const float*>(e[0]);
   __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e[1]);
@@ -138,8 +167,7 @@ extern "C" int mmnas_cast_f32_to_bf16(const float* src, void* dst, long n, mmnas
   if (n == 0) return MMNAS_OK;
   MMNAS_CHECK_ARG(src && dst, "cast: null buffer");
   MMNAS_CHECK_ARG(((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 8) == 0, "cast: buffers must be 16-byte aligned");
-  cast_kernel<<<ew_grid(n >> 2), EW_THREADS, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
-  MMNAS_LAUNCH_CHECK();
+  MMNAS_CUDA(mmnas_launch(cast_kernel, dim3(ew_grid(n >> 2)), dim3(EW_THREADS), 0, (cudaStream_t)stream, src, (__nv_bfloat16*)dst, n));
   return MMNAS_OK;
 }
 
@@ -147,8 +175,7 @@ extern "C" int mmnas_cast_multi(const void* table, int n_chunks, mmnas_stream st
   MMNAS_CHECK_ARG(n_chunks >= 0, "cast_multi: negative chunk count");
   if (n_chunks == 0) return MMNAS_OK;
   MMNAS_CHECK_ARG(table, "cast_multi: null table");
-  cast_multi_kernel<<<n_chunks, EW_THREADS, 0, (cudaStream_t)stream>>>((const long long*)table);
-  MMNAS_LAUNCH_CHECK();
+  MMNAS_CUDA(mmnas_launch(cast_multi_kernel, dim3(n_chunks), dim3(EW_THREADS), 0, (cudaStream_t)stream, (const long long*)table));
   return MMNAS_OK;
 }
 
@@ -158,12 +185,14 @@ extern "C" int mmnas_colsum(int dtype, const void* x, int rows, int cols, long l
   cudaStream_t s = (cudaStream_t)stream;
   MMNAS_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, s));
   if (rows == 0) return MMNAS_OK;
-  int gy = ceil_div(rows, 8 * 16);
-  if (gy > 64) gy = 64;
-  dim3 grid(ceil_div(cols, 32), gy);
-  if (dtype == 0) colsum_kernel<float><<<grid, 256, 0, s>>>((const float*)x, rows, cols, ld, out);
-  else colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, rows, cols, ld, out);
-  MMNAS_LAUNCH_CHECK();
+  const int gx = ceil_div(cols, 256);
+  int gy = ceil_div(rows, 8 * 4);
+  const int cap = gx >= 8 ? 40 : (gx >= 2 ? 148 : 296);     // ~2 CTAs per SM in total
+  if (gy > cap) gy = cap;
+  MMNAS_CHECK_ARG(((uintptr_t)x % 16) == 0, "colsum: x must be 16-byte aligned");
+  dim3 grid(gx, gy);
+  if (dtype == 0) MMNAS_CUDA(mmnas_launch(colsum_kernel<float>, grid, dim3(256), 0, s, (const float*)x, rows, cols, ld, out));
+  else MMNAS_CUDA(mmnas_launch(colsum_kernel<__nv_bfloat16>, grid, dim3(256), 0, s, (const __nv_bfloat16*)x, rows, cols, ld, out));
   return MMNAS_OK;
 }
 
@@ -175,8 +204,7 @@ extern "C" int mmnas_mixed_accum(int K, const float* const* outs, const float* g
   MixedArgs a = {};
   a.K = K; a.gate = gate; a.out = out; a.n = n;
   for (int k = 0; k < K; ++k) { MMNAS_CHECK_ARG(outs[k], "mixed_accum: null candidate output"); a.o[k] = outs[k]; }
-  mixed_accum_kernel<<<ew_grid(n >> 2), EW_THREADS, 0, (cudaStream_t)stream>>>(a);
-  MMNAS_LAUNCH_CHECK();
+  MMNAS_CUDA(mmnas_launch(mixed_accum_kernel, dim3(ew_grid(n >> 2)), dim3(EW_THREADS), 0, (cudaStream_t)stream, a));
   return MMNAS_OK;
 }
 
@@ -194,8 +222,7 @@ extern "C" int mmnas_mixed_alpha_dot(int K, const float* const* outs, const floa
     a.o[k] = outs[k];
     a.d_o[k] = d_outs ? d_outs[k] : nullptr;
   }
-  mixed_alpha_dot_kernel<<<ew_grid(n >> 2), EW_THREADS, 0, s>>>(a);
-  MMNAS_LAUNCH_CHECK();
+  MMNAS_CUDA(mmnas_launch(mixed_alpha_dot_kernel, dim3(ew_grid(n >> 2)), dim3(EW_THREADS), 0, s, a));
   return MMNAS_OK;
 }
 
@@ -204,6 +231,15 @@ extern "C" int mmnas_rng_advance(unsigned long long* state, mmnas_stream stream)
   rng_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state);
   MMNAS_LAUNCH_CHECK();
   return MMNAS_OK;
+}
+
+bool mmnas_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MMNAS_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
 }
 
 // ---- error string / ABI version ------------------------------------------------------------

@@ -9,7 +9,7 @@
 // v2: persistent, warp-specialised, software-pipelined over tiles.
 //   grid = min(#work units, #SMs); a work unit = (split, m-tile, n-tile), n fastest so concurrently running CTAs
 //   share the A tile in L2.  Warp 0 = TMA producer (STAGES-deep smem ring), warp 1 = MMA issuer (one elected lane)
-//   + TMEM allocator, warps 2..5 = epilogue.  TMEM holds TWO accumulator buffers, so the epilogue of unit i
+//   + TMEM allocator, warps 2..9 = epilogue (two warps per TMEM lane quarter, alternating column chunks).  TMEM holds TWO accumulator buffers, so the epilogue of unit i
 //   overlaps the main loop of unit i+1 (v1 paid prologue + fill + epilogue serially per tile and ran at 10 %).
 //   Epilogue: tcgen05.ld (each warp owns the 32 TMEM lanes of its warp%4 quarter) -> padded smem staging ->
 //   re-read row-contiguous, so every global access is a full 64/128-byte row segment; all fused epilogue math
@@ -24,12 +24,13 @@ namespace {
 
 constexpr int BM = 128, BK = 64;
 constexpr int A_TILE_BYTES = BM * BK * 2;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;                      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int EPI_WARPS = 8;
 constexpr int STG_PITCH = 36;                         // floats per staged row (32 + 4 pad: 16B aligned, conflict free)
-constexpr int STG_BYTES = 4 * 32 * STG_PITCH * 4;     // 4 epilogue warps x 32 rows
+constexpr int STG_BYTES = EPI_WARPS * 32 * STG_PITCH * 4;   // one 32-row staging block per epilogue warp
 
 template <int BN> struct Cfg {
-  static constexpr int STAGES = BN == 128 ? 5 : 4;
+  static constexpr int STAGES = BN == 128 ? 5 : 3;
   static constexpr int B_TILE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -116,7 +117,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -141,6 +142,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   if (warp == 0 && lane == 0) {
     // ===== TMA producer =====
+    pdl_wait();                                   // operands come from the previous kernel(s) of the stream
     uint32_t it = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       int z, m0, n0, kb0, nkb;
@@ -165,6 +167,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       }
     }
+    pdl_launch();                                 // all loads issued: the next kernel may start its prologue
   } else if (warp == 1 && lane == 0) {
     // ===== MMA issuer =====
     constexpr uint32_t idesc = make_idesc(A_MN, B_MN, BM, BN);
@@ -195,8 +198,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp >= 2) {
     // ===== epilogue: TMEM -> registers -> smem staging -> coalesced global =====
+    // Eight warps: warp%4 selects the TMEM lane quarter (hardware rule), the two warps of a quarter alternate
+    // over the 32-column chunks, so the epilogue keeps up with a 128 x BN x 512 main loop.
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32)
-    float* stg = staging + quarter * (32 * STG_PITCH);
+    const int half = (warp - 2) >> 2;             // 0: warps 2..5, 1: warps 6..9
+    pdl_wait();                                   // this warp reads (accumulate / aux / bias) and writes global memory
+    float* stg = staging + (warp - 2) * (32 * STG_PITCH);
     const uint64_t key = ep.use_drop ? drop_key(ep.drop) : 0;
     const int sub_r = lane >> 3, col4 = (lane & 7) * 4;
     uint32_t j = 0;
@@ -209,7 +216,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const bool add_bias = ep.bias != nullptr && z == 0;
       const int row_base = m0 + quarter * 32;
 #pragma unroll 1
-      for (int cc = 0; cc < BN / 32; ++cc) {
+      for (int cc = half; cc < BN / 32; cc += 2) {
         const int col0 = n0 + cc * 32;
         if (col0 >= ep.N) break;                  // warp-uniform (N % 32 == 0)
         uint32_t r[32];
@@ -274,8 +281,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcEpilogue& ep, c
   }
   const int units = ep.tiles_m * ep.tiles_n * ep.split_k;
   const int grid = units < num_sms() ? units : num_sms();
-  gemm_bf16_tc_kernel<A_MN, B_MN, BN><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, s>>>(ta, tb, ep);
-  MMNAS_LAUNCH_CHECK();
+  MMNAS_CUDA(mmnas_launch(gemm_bf16_tc_kernel<A_MN, B_MN, BN>, dim3(grid), dim3(NUM_THREADS), Cfg<BN>::SMEM_BYTES, s, ta, tb, ep));
   return MMNAS_OK;
 }
 

@@ -29,6 +29,7 @@ ln_fwd_kernel(int rows, int H, const float* __restrict__ x, float* __restrict__ 
               const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
               float* __restrict__ out, __nv_bfloat16* __restrict__ out16,
               float* __restrict__ mean_out, float* __restrict__ sigma_out, DropCfg drop) {
+  pdl_wait(); pdl_launch();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * ROWS_PER_CTA + warp;
   if (row >= rows) return;
@@ -105,6 +106,7 @@ ln_bwd_kernel(int rows, int H, const float* __restrict__ dout, const float* __re
               const float* __restrict__ mean_in, const float* __restrict__ sigma_in,
               const float* __restrict__ gamma, float eps, float* __restrict__ dz, TB* __restrict__ dbranch,
               float* __restrict__ dgamma, float* __restrict__ dbeta, DropCfg drop) {
+  pdl_wait(); pdl_launch();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool norm = gamma != nullptr;
   const bool use_drop = drop.state != nullptr && drop.thresh > 0;
@@ -225,7 +227,7 @@ extern "C" int mmnas_ln_residual_fwd(int rows, int H, const float* x, float* bra
   cudaStream_t s = (cudaStream_t)stream;
   const DropCfg d = make_drop(rng_state, salt, p);
   __nv_bfloat16* o16 = (__nv_bfloat16*)out_bf16;
-#define LN_FWD(NV, EX) ln_fwd_kernel<NV, EX><<<grid, block, 0, s>>>(rows, H, x, branch, gamma, beta, eps, out, o16, mean, sigma, d)
+#define LN_FWD(NV, EX) MMNAS_CUDA(mmnas_launch(ln_fwd_kernel<NV, EX>, grid, block, 0, s, rows, H, x, branch, gamma, beta, eps, out, o16, mean, sigma, d))
   if (H == 256) LN_FWD(2, true);
   else if (H == 512) LN_FWD(4, true);
   else if (H == 1024) LN_FWD(8, true);
@@ -254,7 +256,7 @@ extern "C" int mmnas_ln_residual_bwd(int rows, int H, const float* dout, const f
   if (ctas > 148 * 4) ctas = 148 * 4;   // grid-stride over rows: column partials stay in registers
   dim3 grid(ctas), block(ROWS_PER_CTA * 32);
   cudaStream_t s = (cudaStream_t)stream;
-#define LN_BWD(TB, NV, EX) ln_bwd_kernel<TB, NV, EX><<<grid, block, smem, s>>>(rows, H, dout, z, mean, sigma, gamma, eps, dz, (TB*)dbranch, dgamma, dbeta, d)
+#define LN_BWD(TB, NV, EX) MMNAS_CUDA(mmnas_launch(ln_bwd_kernel<TB, NV, EX>, grid, block, smem, s, rows, H, dout, z, mean, sigma, gamma, eps, dz, (TB*)dbranch, dgamma, dbeta, d))
 #define LN_BWD_H(TB)                                  \
   do {                                                \
     if (H == 256) LN_BWD(TB, 2, true);                \

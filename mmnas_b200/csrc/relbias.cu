@@ -42,6 +42,7 @@ struct RelArgs {
 
 template <int HEADS, bool DENSE>
 __global__ void __launch_bounds__(256) relbias_fwd_kernel(RelArgs a) {
+  pdl_wait(); pdl_launch();
   const unsigned pair = blockIdx.x * 256u + threadIdx.x;
   if (pair >= a.pairs) return;
   float r[HEADS];
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(TILE) relbias_bwd_kernel(RelArgs a) {
   float* Dp = DE + R * EP;           // [TILE][HP] d pre_r
   constexpr int HP = HEADS < 4 ? 4 : HEADS;
   float* G = Dp + TILE * HP;         // [TILE][4]
+  pdl_wait(); pdl_launch();
   const int t = threadIdx.x;
   const int c_own = t & 63, half = t >> 6;      // phase B: column and which half of the tile's pairs
   float accWr[HEADS], accWy[4] = {0.f, 0.f, 0.f, 0.f}, accby = 0.f, accbr = 0.f;
@@ -224,9 +226,8 @@ int stage_weights(int heads, const float* Wy, const float* by, const float* Wr, 
 template <int HEADS>
 int launch_fwd(const RelArgs& a, cudaStream_t s) {
   const unsigned grid = (a.pairs + 255u) / 256u;
-  if (a.rel) relbias_fwd_kernel<HEADS, true><<<grid, 256, 0, s>>>(a);
-  else relbias_fwd_kernel<HEADS, false><<<grid, 256, 0, s>>>(a);
-  MMNAS_LAUNCH_CHECK();
+  if (a.rel) MMNAS_CUDA(mmnas_launch(relbias_fwd_kernel<HEADS, true>, dim3(grid), dim3(256), 0, s, a));
+  else MMNAS_CUDA(mmnas_launch(relbias_fwd_kernel<HEADS, false>, dim3(grid), dim3(256), 0, s, a));
   return MMNAS_OK;
 }
 
@@ -241,9 +242,8 @@ int launch_bwd(const RelArgs& a, cudaStream_t s) {
   }
   const unsigned ntiles = (a.pairs + TILE - 1) / TILE;
   const unsigned grid = ntiles < 148u * 3u ? ntiles : 148u * 3u;
-  if (a.rel) relbias_bwd_kernel<HEADS, true><<<grid, TILE, smem, s>>>(a);
-  else relbias_bwd_kernel<HEADS, false><<<grid, TILE, smem, s>>>(a);
-  MMNAS_LAUNCH_CHECK();
+  if (a.rel) MMNAS_CUDA(mmnas_launch(relbias_bwd_kernel<HEADS, true>, dim3(grid), dim3(TILE), smem, s, a));
+  else MMNAS_CUDA(mmnas_launch(relbias_bwd_kernel<HEADS, false>, dim3(grid), dim3(TILE), smem, s, a));
   return MMNAS_OK;
 }
 
