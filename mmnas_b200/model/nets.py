@@ -101,6 +101,8 @@ class _NetBase(nn.Module):
             self.bboxfeat_linear = nn.Linear(5, __C.BBOXFEAT_EMB_SIZE)
             feat += __C.BBOXFEAT_EMB_SIZE
         self.imgfeat_linear = nn.Linear(feat, __C.HSIZE)
+        if task == 'itm' and not self.SEARCH:       # full_itm.py:75 creates it before the backbone (same-seed init parity)
+            self.linear_y_rel = nn.Linear(4, __C.REL_SIZE)
         self.backnone = self.BACKBONE(__C)
         self.attflat_x = AttFlat(__C)
         if task == 'vgd':       # full_vgd.py:83-87
@@ -114,7 +116,8 @@ class _NetBase(nn.Module):
             self.proj = nn.Linear(__C.ATTFLAT_OUT_SIZE, init_dict['ans_size'] if task == 'vqa' else 1)
         if self.SEARCH:
             self.linear_x_rel = nn.Linear(3, __C.REL_SIZE)
-        self.linear_y_rel = nn.Linear(4, __C.REL_SIZE)
+        if not hasattr(self, 'linear_y_rel'):
+            self.linear_y_rel = nn.Linear(4, __C.REL_SIZE)
 
     def forward(self, input):
         frcn_feat, bbox_feat, y_rel, ques_ix, x_rel = input

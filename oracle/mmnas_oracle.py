@@ -220,6 +220,32 @@ def head_vqa(P, x, y, x_mask, y_mask, p=0.0, training=False):
     return F.linear(xy, P['proj.weight'], P['proj.bias'])
 
 
+def head_vgd(P, x, y, x_mask, scores_loss='kld', p=0.0, training=False):
+    """full_vgd.py:105-112: per-region scores (log-softmax over regions for the KLD loss) and box regression."""
+    xy = att_flat(P, 'attflat_x.', x, x_mask, p, training).unsqueeze(1) + F.linear(y, P['attfc_y.weight'], P['attfc_y.bias'])
+    xy = layer_norm(xy, P['proj_norm.a_2'], P['proj_norm.b_2'])
+    scores = F.linear(xy, P['proj_scores.weight'], P['proj_scores.bias']).squeeze(-1)
+    if scores_loss == 'kld':
+        scores = F.log_softmax(scores, dim=-1)
+    return scores, F.linear(xy, P['proj_reg.weight'], P['proj_reg.bias'])
+
+
+def head_itm(P, x, y, x_mask, y_mask, p=0.0, training=False):
+    """full_itm.py:105-110: one matching logit per (image, caption) pair, through a sigmoid."""
+    return torch.sigmoid(head_vqa(P, x, y, x_mask, y_mask, p, training).squeeze(-1))
+
+
+def net_full(P, inputs, genotype, task='vqa', scores_loss='kld', p=0.0, training=False):
+    """Net_Full of full_vqa.py / full_vgd.py / full_itm.py: same stem and backbone, task-specific head."""
+    x, y = net_full_vqa(P, inputs, genotype, p, training, return_backbone=True)
+    x_mask, y_mask = make_mask(inputs[3].unsqueeze(2)), make_mask(inputs[0])
+    if task == 'vgd':
+        return head_vgd(P, x, y, x_mask, scores_loss, p, training)
+    if task == 'itm':
+        return head_itm(P, x, y, x_mask, y_mask, p, training)
+    return head_vqa(P, x, y, x_mask, y_mask, p, training)
+
+
 def net_full_vqa(P, inputs, genotype, p=0.0, training=False, return_backbone=False):
     """Net_Full (full_vqa.py:56-114) on the genotype {'enc': [[op]...], 'dec': [[op]...]}."""
     x, y, x_mask, y_mask, x_rel, y_rel = stem_vqa(P, inputs)

@@ -153,6 +153,37 @@ def golden_net_full(mods):
     np.savez_compressed(os.path.join(OUT, 'net_full_h64.npz'), **npify(rec))
 
 
+def golden_net_full_task(task):
+    """Tiny Net_Full of full_vgd.py / full_itm.py (VGD: 7-token queries, every region valid, KLD log-softmax scores +
+    box regression; ITM: sigmoid matching score): outputs and every gradient of a fixed linear functional of them."""
+    import importlib
+    Net_Full = importlib.import_module('mmnas.model.full_' + task).Net_Full
+    geno = {'enc': [['self_att_64'], ['feed_forward']],
+            'dec': [['guided_att_64'], ['rel_self_att_64'], ['guided_att_64'], ['feed_forward']]}
+    h, b, ny, nx, vocab = 64, 3, 6, 7, 30
+    torch.manual_seed(888)
+    np.random.seed(888)
+    init = {'token_size': vocab, 'ans_size': 5, 'pretrained_emb': (0.1 * np.random.randn(vocab, 16)).astype(np.float32)}
+    cfg = net_cfg(h, genotype=geno)
+    cfg.SCORES_LOSS = 'kld'
+    net = Net_Full(cfg, init)
+    inputs = synth_inputs(b, ny, nx, 32, vocab, 7)
+    g = torch.Generator().manual_seed(8)
+    outs = net(inputs)
+    outs = outs if isinstance(outs, tuple) else (outs,)
+    ws = [torch.randn(o.shape, generator=g) for o in outs]
+    sum((o * w).sum() for o, w in zip(outs, ws)).backward()
+    rec = {'frcn': inputs[0], 'bbox': inputs[1], 'rel': inputs[2], 'ques': inputs[3], 'rel_q': inputs[4],
+           'genotype': np.array(repr(geno))}
+    for i, (o, w) in enumerate(zip(outs, ws)):
+        rec['out%d' % i] = o
+        rec['w%d' % i] = w
+    for n_, p_ in net.named_parameters():
+        rec['p.' + n_] = p_
+        rec['g.' + n_] = p_.grad
+    np.savez_compressed(os.path.join(OUT, 'net_full_%s_h64.npz' % task), **npify(rec))
+
+
 def golden_net_search(mods):
     """Tiny Net_Search-VQA arch step (search_vqa.py:317-332, MODE='full'): loss, alpha_gate grads,
     alpha_prob grads after set_arch_param_grad, alpha_prob after one alpha Adam step, genotype."""
@@ -232,6 +263,8 @@ def main():
     golden_mixed(mods)
     golden_net_full(mods)
     golden_net_search(mods)
+    golden_net_full_task('vgd')
+    golden_net_full_task('itm')
     golden_geometry()
     for f in sorted(os.listdir(OUT)):
         if f.endswith('.npz'):

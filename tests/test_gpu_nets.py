@@ -197,3 +197,59 @@ def test_search_step_weight_and_arch():
     assert all(m.candidate_ops[i] is not None for m in net.redundant_modules for i in range(m.n_choices))
     g = net.genotype()
     assert len(g['enc']) == 12 and len(g['dec']) == 18
+
+
+@pytest.mark.parametrize('task', ['vgd', 'itm'])
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_net_full_vgd_itm_match_reference_golden(mode, task):
+    """BASELINE configs 4 / 5 at toy size: the VGD net (per-region log-softmax scores + box regression) and the ITM net
+    (sigmoid matching score) of the unmodified reference, forward and every gradient."""
+    import mmnas_b200
+    from mmnas_b200.model.nets import Net_Full
+    r = load_golden('net_full_%s_h64.npz' % task)
+    cfg = tiny_cfg(literal(r, 'genotype'))
+    cfg.SCORES_LOSS = 'kld'
+    net = Net_Full(cfg, {'token_size': 30, 'ans_size': 5, 'pretrained_emb': np.zeros((30, 16), np.float32)}, task=task)
+    net.load_state_dict(params_of(r))
+    net = net.to(DEV).train()
+    with mmnas_b200.precision(mode):
+        outs = net(dev_inputs(r))
+        outs = outs if isinstance(outs, tuple) else (outs,)
+        sum((o * r['w%d' % i].to(DEV)).sum() for i, o in enumerate(outs)).backward()
+    pr = Parity('golden/net_full_%s/%s' % (task, mode))
+    for i, o in enumerate(outs):
+        pr.add('out%d' % i, o, r['out%d' % i], TOL[mode])
+    floor = grad_floor(r)
+    for n_, p_ in net.named_parameters():
+        pr.add(n_, p_.grad, r['g.' + n_], GTOL[mode] * (2 if mode == 'bf16' else 1), floor, metric=GMETRIC[mode])
+    pr.check()
+
+
+@pytest.mark.parametrize('task,arch,ny,nx', [('vgd', 'mmnas_vgd', 100, 15), ('itm', 'mmnas_itm', 36, 50)])
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_vgd_itm_nets_at_baseline_shapes_match_oracle(mode, task, arch, ny, nx):
+    """Configs G (RefCOCO-shaped: 100 valid regions, 15-token queries, RSA-heavy arch mmnas_vgd) and I (Flickr30K-shaped:
+    36 regions, 50-token captions, arch mmnas_itm) at H=512: outputs against the float64 CPU oracle."""
+    import mmnas_b200
+    from mmnas_b200 import genotypes
+    from mmnas_b200.data.synthetic import Cfg, SynthSpec, make_batch, init_dict
+    from mmnas_b200.model.nets import Net_Full
+    torch.manual_seed(888)
+    spec = SynthSpec(task=task, batch=4, n_regions=ny, n_tokens=nx, vocab=1000, n_ans=10, ragged=(task != 'vgd'))
+    cfg = Cfg(genotype=genotypes.shipped(arch), DROPOUT_R=0.0, SCORES_LOSS='kld')
+    inputs, _ = make_batch(spec)
+    net = Net_Full(cfg, init_dict(spec), task=task).train()
+    with torch.no_grad():
+        condition_rsa_(dict(net.named_parameters()))
+    P = O.leaf_params(net.state_dict(), torch.float64, requires_grad=False)
+    inp64 = tuple(t.double() if t.is_floating_point() else t for t in inputs)
+    ref = O.net_full(P, inp64, cfg.GENOTYPE, task=task)
+    ref = ref if isinstance(ref, tuple) else (ref,)
+    net = net.to(DEV)
+    with mmnas_b200.precision(mode), torch.no_grad():
+        outs = net(tuple(t.to(DEV) for t in inputs))
+    outs = outs if isinstance(outs, tuple) else (outs,)
+    pr = Parity('oracle/net_full_%s_H512/%s' % (task, mode))
+    for i, (o, rf) in enumerate(zip(outs, ref)):
+        pr.add('out%d' % i, o, rf, TOL[mode])
+    pr.check()

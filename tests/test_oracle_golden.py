@@ -120,3 +120,19 @@ def test_oracle_matches_live_reference_at_bench_shapes():
         ref = op(x, y, xm, ym, rel)
         out = O.op_forward(name, dict(op.state_dict()), '', x, y, xm, ym, rel)
         assert normwise(out, ref) < TOL, name
+
+
+@pytest.mark.parametrize('task', ['vgd', 'itm'])
+def test_net_full_vgd_itm_match_golden(task):
+    r = load_golden('net_full_%s_h64.npz' % task)
+    P = O.leaf_params(params_of(r))
+    inputs = (r['frcn'], r['bbox'], r['rel'], r['ques'], r['rel_q'])
+    outs = O.net_full(P, inputs, literal(r, 'genotype'), task=task)
+    outs = outs if isinstance(outs, tuple) else (outs,)
+    for i, o in enumerate(outs):
+        assert normwise(o, r['out%d' % i]) < TOL
+    sum((o * r['w%d' % i]).sum() for i, o in enumerate(outs)).backward()
+    floor = grad_floor(r)
+    for k, p in P.items():
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        assert normwise(g, r['g.' + k], floor) < 5e-6, k
