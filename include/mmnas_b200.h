@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MMNAS_B200_ABI_VERSION 1
+#define MMNAS_B200_ABI_VERSION 2
 
 typedef void* mmnas_stream;
 
@@ -99,8 +99,8 @@ int mmnas_cast_f32_to_bf16(const float* src, void* dst, long n, mmnas_stream str
 /* Batched cast: `table` is a DEVICE array of n_chunks triples of int64 {src float*, dst bf16*, count}; each chunk has
  * count <= 4096, count % 4 == 0, 16-byte aligned pointers.  Refreshes every bf16 weight shadow of a model in one launch. */
 int mmnas_cast_multi(const void* table, int n_chunks, mmnas_stream stream);
-/* out[c] = sum_r x[r,c] (bias gradients); out is overwritten. */
-int mmnas_colsum(int dtype, const void* x, int rows, int cols, long ld, float* out, mmnas_stream stream);
+/* out[c] (+)= sum_r x[r,c] (bias gradients); accumulate == 0 overwrites out, 1 adds into it (gradient buffers). */
+int mmnas_colsum(int dtype, const void* x, int rows, int cols, long ld, float* out, int accumulate, mmnas_stream stream);
 /* state[1] += 1: call once per training step so every step draws fresh dropout masks (graph-capturable). */
 int mmnas_rng_advance(unsigned long long* state, mmnas_stream stream);
 

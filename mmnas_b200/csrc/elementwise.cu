@@ -179,11 +179,12 @@ extern "C" int mmnas_cast_multi(const void* table, int n_chunks, mmnas_stream st
   return MMNAS_OK;
 }
 
-extern "C" int mmnas_colsum(int dtype, const void* x, int rows, int cols, long ld, float* out, mmnas_stream stream) {
+extern "C" int mmnas_colsum(int dtype, const void* x, int rows, int cols, long ld, float* out, int accumulate,
+                            mmnas_stream stream) {
   MMNAS_CHECK_ARG(dtype == 0 || dtype == 1, "colsum: dtype");
   MMNAS_CHECK_ARG(rows >= 0 && cols > 0 && x && out, "colsum: bad argument");
   cudaStream_t s = (cudaStream_t)stream;
-  MMNAS_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, s));
+  if (!accumulate) MMNAS_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, s));
   if (rows == 0) return MMNAS_OK;
   const int gx = ceil_div(cols, 256);
   int gy = ceil_div(rows, 8 * 4);

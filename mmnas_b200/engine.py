@@ -79,9 +79,12 @@ class BucketReducer:
         self._launched = [False] * len(self.buckets)
         self._works = []
         self._avg = None
+        self._index = {id(p): i for i, p in enumerate(self.fg.params)}
+        self._hooks = [self._make_hook(i) for i in range(len(self.fg.params))]
+        self._armed = False
         if self.enabled:
             for i, p in enumerate(self.fg.params):
-                p.register_post_accumulate_grad_hook(self._make_hook(i))
+                p.register_post_accumulate_grad_hook(self._hooks[i])
         self.reset()
 
     def _make_hook(self, i):
@@ -93,6 +96,12 @@ class BucketReducer:
             if self._pending[b] == 0:
                 self._launch(b)
         return hook
+
+    def notify(self, param):
+        """Same as the autograd hook, for gradients a block backward accumulated straight into p.grad."""
+        i = self._index.get(id(param))
+        if i is not None and self.enabled:
+            self._hooks[i](param)
 
     def reset(self):
         """Arm for one backward pass."""
@@ -235,12 +244,14 @@ class TrainStep:
         if runtime.get_precision() == 'bf16':
             self.shadows.refresh()
             runtime.shadows_fresh = True
+        runtime.direct_grads, runtime.grad_listener = True, self.reducer.notify
         try:
             pred = self.net(inputs)
             loss = self.loss_fn(pred, target)
             loss.backward()
         finally:
             runtime.shadows_fresh = False
+            runtime.direct_grads, runtime.grad_listener = False, None
         self.reducer.finish()
         self.optim.clip_and_step()
         return loss.detach()
@@ -298,8 +309,12 @@ class SearchStep:
         self.grads.zero()                # net.zero_grad() + the reference's 0*sum(params) dummy terms
         self.reducer.reset()
         runtime.advance(target.device)
-        loss = self.loss_fn(self.net(inputs), target)
-        loss.backward()
+        runtime.direct_grads, runtime.grad_listener = True, self.reducer.notify
+        try:
+            loss = self.loss_fn(self.net(inputs), target)
+            loss.backward()
+        finally:
+            runtime.direct_grads, runtime.grad_listener = False, None
         self.reducer.finish()
         return loss.detach()
 

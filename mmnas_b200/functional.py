@@ -15,6 +15,7 @@ import torch
 from torch.autograd import Function
 
 from . import kernels as K
+from . import runtime
 from ._lib import require_cuda
 
 HEAD = 64
@@ -45,6 +46,57 @@ def _empty(shape, dtype, dev):
     return torch.empty(shape, dtype=dtype, device=dev)
 
 
+def _grad_target(params):
+    """When the engine asked for direct gradient accumulation (runtime.direct_grads) and `params` own preset,
+    contiguous fp32 .grad buffers that sit back to back in memory (engine.FlatGrads), return one fp32 view
+    [sum rows, cols] over those buffers; the backward then accumulates into it (split-K red.add / C += ...) and returns
+    None for these parameters, which removes autograd's per-parameter `grad += new` kernels and the zero-filled
+    temporaries.  Otherwise None."""
+    if not runtime.direct_grads:
+        return None
+    g0 = params[0].grad
+    if g0 is None:
+        return None
+    rows, ptr = 0, g0.data_ptr()
+    for p in params:
+        g = p.grad
+        if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.data_ptr() != ptr:
+            return None
+        ptr += 4 * g.numel()
+        rows += p.shape[0]
+    shape = (rows,) + tuple(params[0].shape[1:])
+    return torch.as_strided(g0, shape, tuple(params[0].stride()) if params[0].dim() > 1 else (1,))
+
+
+class _Sink:
+    """Destination of a parameter gradient: the parameters' own .grad memory (direct mode: the kernel accumulates,
+    autograd gets None) or a fresh buffer returned to autograd."""
+
+    def __init__(self, params, dev):
+        self.params = params
+        self.dev = dev
+        self.target = _grad_target(params)
+        self.direct = self.target is not None
+        self.buf = self.target
+
+    def prepare(self, zero):
+        if not self.direct:
+            rows = sum(p.shape[0] for p in self.params)
+            shape = (rows,) + tuple(self.params[0].shape[1:])
+            self.buf = (torch.zeros if zero else torch.empty)(shape, dtype=torch.float32, device=self.dev)
+        return self
+
+    def grads(self):
+        if self.direct:
+            runtime.notify_grads(self.params)
+            return (None,) * len(self.params)
+        out, r = [], 0
+        for p in self.params:
+            out.append(self.buf[r:r + p.shape[0]])
+            r += p.shape[0]
+        return tuple(out)
+
+
 def _bf16(t, shadow):
     if shadow is not None:
         return shadow
@@ -60,6 +112,7 @@ class AttBlockFn(Function):
     @staticmethod
     def forward(ctx, x, kv, Wq, Wk, Wv, Wm, a2, b2, rel, g4, Wy, by, Wr, br, cfg):
         require_cuda(x, kv, Wq)
+        ctx.set_materialize_grads(False)      # no zero-filled gradient tensor for the bf16 shadow output
         dev = x.device
         x = x.contiguous()
         B, Nq, H = x.shape
@@ -80,21 +133,21 @@ class AttBlockFn(Function):
             kv16 = x16 if self_att else _bf16(kvt, cfg.kv16)
         # --- projections
         if self_att:
-            qkv = _empty((Mq, 3 * I), adt, dev)
-            q, k, v = qkv[:, :I], qkv[:, I:2 * I], qkv[:, 2 * I:]
+            qkv = _empty((Mq, 3 * I), adt, dev)          # columns [v | k | q]: the parameters' registration order
+            v, k, q = qkv[:, :I], qkv[:, I:2 * I], qkv[:, 2 * I:]
             kvb = None
             if bf:
-                K.gemm_bf16(Mq, 3 * I, H, x16, H, 0, cfg.w16['qkv'], H, 0, qkv, 3 * I)
+                K.gemm_bf16(Mq, 3 * I, H, x16, H, 0, cfg.w16['vkq'], H, 0, qkv, 3 * I)
             else:
                 for W, dst in ((Wq, q), (Wk, k), (Wv, v)):
                     K.gemm_f32(Mq, I, H, x, H, 1, W, 1, H, dst, 3 * I)
         else:
             qkv = _empty((Mq, I), adt, dev)
-            kvb = _empty((Mk, 2 * I), adt, dev)
-            q, k, v = qkv, kvb[:, :I], kvb[:, I:]
+            kvb = _empty((Mk, 2 * I), adt, dev)          # columns [v | k]
+            q, v, k = qkv, kvb[:, :I], kvb[:, I:]
             if bf:
                 K.gemm_bf16(Mq, I, H, x16, H, 0, cfg.w16['q'], H, 0, qkv, I)
-                K.gemm_bf16(Mk, 2 * I, H, kv16, H, 0, cfg.w16['kv'], H, 0, kvb, 2 * I)
+                K.gemm_bf16(Mk, 2 * I, H, kv16, H, 0, cfg.w16['vk'], H, 0, kvb, 2 * I)
             else:
                 K.gemm_f32(Mq, I, H, x, H, 1, Wq, 1, H, q, I)
                 K.gemm_f32(Mk, I, H, kvt, H, 1, Wk, 1, H, k, 2 * I)
@@ -128,6 +181,7 @@ class AttBlockFn(Function):
         K.ln_residual_fwd(Mq, H, x if cfg.residual else None, branch, a2, b2, cfg.eps, out, out16, mean, sigma, d_out)
 
         ctx.cfg, ctx.dims = cfg, (B, Nq, Nk, H, I, heads, R, self_att)
+        ctx.b2 = b2
         ctx.save_for_backward(x, kvt, Wq, Wk, Wv, Wm, a2, rel, g4, Wy, by, Wr, br, qkv, kvb, bias, atted, branch, mean,
                               sigma, x16, kv16)
         if bf:
@@ -137,6 +191,8 @@ class AttBlockFn(Function):
 
     @staticmethod
     def backward(ctx, dout, _unused=None):
+        if dout is None:
+            return (None,) * 15
         cfg = ctx.cfg
         B, Nq, Nk, H, I, heads, R, self_att = ctx.dims
         (x, kvt, Wq, Wk, Wv, Wm, a2, rel, g4, Wy, by, Wr, br, qkv, kvb, bias, atted, z, mean, sigma, x16,
@@ -150,100 +206,98 @@ class AttBlockFn(Function):
         norm = a2 is not None
         dout = dout.contiguous()
 
+        def wgrad(sink, M_, N_, K_, A, lda, Bm, ldb, a32, b32):
+            """sink (+)= A^T Bm over K_ tokens.  bf16: operands [K_, M_] / [K_, N_] read MN-major; fp32: strided FFMA."""
+            if bf:
+                sk = _split_k(M_, N_, K_)
+                sink.prepare(zero=sk > 1)
+                K.gemm_bf16(M_, N_, K_, A, lda, 1, Bm, ldb, 1, sink.buf, N_, split_k=sk, accumulate=sink.direct and sk == 1)
+            else:
+                sink.prepare(zero=False)
+                K.gemm_f32(M_, N_, K_, a32, 1, lda, b32, ldb, 1, sink.buf, N_, accumulate=sink.direct)
+
         # --- LayerNorm + residual + output-dropout backward
         dz = _empty((Mq, H), torch.float32, dev) if cfg.residual else None
         separate = bf or d_out.active or not cfg.residual
         dbranch = _empty((Mq, H), adt, dev) if separate else None
-        da2 = torch.zeros(H, dtype=torch.float32, device=dev) if norm else None
-        db2 = torch.zeros(H, dtype=torch.float32, device=dev) if norm else None
-        K.ln_residual_bwd(Mq, H, dout, z, mean, sigma, a2, cfg.eps, dz, dbranch, da2, db2, d_out)
+        s_a2 = s_b2 = None
+        if norm:
+            s_a2, s_b2 = _Sink([a2], dev).prepare(True), _Sink([ctx.b2], dev).prepare(True)
+        K.ln_residual_bwd(Mq, H, dout, z, mean, sigma, a2, cfg.eps, dz, dbranch, s_a2.buf if norm else None,
+                          s_b2.buf if norm else None, d_out)
         if dbranch is None:
             dbranch = dz
         # --- merge projection backward
         datt = _empty((Mq, I), adt, dev)
+        s_m = _Sink([Wm], dev)
+        wgrad(s_m, H, I, Mq, dbranch, H, atted, I, dbranch, atted)
         if bf:
-            dWm = torch.zeros((H, I), dtype=torch.float32, device=dev)
-            K.gemm_bf16(H, I, Mq, dbranch, H, 1, atted, I, 1, dWm, I, split_k=_split_k(H, I, Mq))
             K.gemm_bf16(Mq, I, H, dbranch, H, 0, cfg.w16['m'], I, 1, datt, I)
         else:
-            dWm = _empty((H, I), torch.float32, dev)
-            K.gemm_f32(H, I, Mq, dbranch, 1, H, atted, I, 1, dWm, I)
             K.gemm_f32(Mq, I, H, dbranch, H, 1, Wm, I, 1, datt, I)
-        # --- attention core backward
+        # --- attention core backward (fused buffers keep the parameters' registration order v, k, q)
         if self_att:
-            q, k, v = qkv[:, :I], qkv[:, I:2 * I], qkv[:, 2 * I:]
+            v, k, q = qkv[:, :I], qkv[:, I:2 * I], qkv[:, 2 * I:]
             dqkv = _empty((Mq, 3 * I), adt, dev)
-            dq, dk, dv = dqkv[:, :I], dqkv[:, I:2 * I], dqkv[:, 2 * I:]
+            dv, dk, dq = dqkv[:, :I], dqkv[:, I:2 * I], dqkv[:, 2 * I:]
             dkvb = None
         else:
-            q, k, v = qkv, kvb[:, :I], kvb[:, I:]
+            q, v, k = qkv, kvb[:, :I], kvb[:, I:]
             dqkv = _empty((Mq, I), adt, dev)
             dkvb = _empty((Mk, 2 * I), adt, dev)
-            dq, dk, dv = dqkv, dkvb[:, :I], dkvb[:, I:]
+            dq, dv, dk = dqkv, dkvb[:, :I], dkvb[:, I:]
         dbias = _empty((B, heads, Nq, Nk), torch.float32, dev) if bias is not None else None
         K.attn_bwd(B, heads, Nq, Nk, q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
                    cfg.kmask, bias, atted, I, datt, I, dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0),
                    dv.data_ptr(), dv.stride(0), dbias, scale, d_att)
-        # --- geometry-bias backward
-        drel = dWy = dby = dWr = dbr = None
+        # --- geometry-bias backward (kernels accumulate with atomics)
+        drel = None
+        g_Wy = g_by = g_Wr = g_br = None
         if bias is not None:
-            dWr = torch.zeros_like(Wr)
-            dbr = torch.zeros_like(br)
+            s_Wr, s_br = _Sink([Wr], dev).prepare(True), _Sink([br], dev).prepare(True)
             if g4 is not None:
-                dWy = torch.zeros_like(Wy)
-                dby = torch.zeros_like(by)
-                K.relbias_bwd(B, Nq, heads, R, None, g4, Wy, by, Wr, br, dbias, None, dWy, dby, dWr, dbr)
+                s_Wy, s_by = _Sink([Wy], dev).prepare(True), _Sink([by], dev).prepare(True)
+                K.relbias_bwd(B, Nq, heads, R, None, g4, Wy, by, Wr, br, dbias, None, s_Wy.buf, s_by.buf, s_Wr.buf, s_br.buf)
+                g_Wy, g_by = s_Wy.grads()[0], s_by.grads()[0]
             else:
                 drel = torch.empty_like(rel)
-                K.relbias_bwd(B, Nq, heads, R, rel, None, None, None, Wr, br, dbias, drel, None, None, dWr, dbr)
+                K.relbias_bwd(B, Nq, heads, R, rel, None, None, None, Wr, br, dbias, drel, None, None, s_Wr.buf, s_br.buf)
+            g_Wr, g_br = s_Wr.grads()[0], s_br.grads()[0]
         # --- projection backward: weight gradients and input gradients
         dkv_in = None
+        fresh_dz = dz is None
+        if fresh_dz:
+            dz = _empty((Mq, H), torch.float32, dev)
         if self_att:
+            s_vkq = _Sink([Wv, Wk, Wq], dev)
+            wgrad(s_vkq, 3 * I, H, Mq, dqkv, 3 * I, x16, H, dqkv, x)
+            g_Wv, g_Wk, g_Wq = s_vkq.grads()
             if bf:
-                dW = torch.zeros((3 * I, H), dtype=torch.float32, device=dev)
-                K.gemm_bf16(3 * I, H, Mq, dqkv, 3 * I, 1, x16, H, 1, dW, H, split_k=_split_k(3 * I, H, Mq))
-                if dz is None:
-                    dz = _empty((Mq, H), torch.float32, dev)
-                    K.gemm_bf16(Mq, H, 3 * I, dqkv, 3 * I, 0, cfg.w16['qkv'], H, 1, dz, H)
-                else:
-                    K.gemm_bf16(Mq, H, 3 * I, dqkv, 3 * I, 0, cfg.w16['qkv'], H, 1, dz, H, accumulate=True)
+                K.gemm_bf16(Mq, H, 3 * I, dqkv, 3 * I, 0, cfg.w16['vkq'], H, 1, dz, H, accumulate=not fresh_dz)
             else:
-                dW = _empty((3 * I, H), torch.float32, dev)
-                K.gemm_f32(3 * I, H, Mq, dqkv, 1, 3 * I, x, H, 1, dW, H)
-                acc = dz is not None
-                if dz is None:
-                    dz = _empty((Mq, H), torch.float32, dev)
-                for W, d in ((Wq, dq), (Wk, dk), (Wv, dv)):
+                acc = not fresh_dz
+                for W, d in ((Wv, dv), (Wk, dk), (Wq, dq)):
                     K.gemm_f32(Mq, H, I, d, 3 * I, 1, W, H, 1, dz, H, accumulate=acc)
                     acc = True
-            dWq, dWk, dWv = dW[:I], dW[I:2 * I], dW[2 * I:]
         else:
             dkv_in = _empty((Mk, H), torch.float32, dev)
+            s_q, s_vk = _Sink([Wq], dev), _Sink([Wv, Wk], dev)
+            wgrad(s_q, I, H, Mq, dqkv, I, x16, H, dqkv, x)
+            wgrad(s_vk, 2 * I, H, Mk, dkvb, 2 * I, kv16, H, dkvb, kvt)
+            g_Wq, = s_q.grads()
+            g_Wv, g_Wk = s_vk.grads()
             if bf:
-                dWq = torch.zeros((I, H), dtype=torch.float32, device=dev)
-                dWkv = torch.zeros((2 * I, H), dtype=torch.float32, device=dev)
-                K.gemm_bf16(I, H, Mq, dqkv, I, 1, x16, H, 1, dWq, H, split_k=_split_k(I, H, Mq))
-                K.gemm_bf16(2 * I, H, Mk, dkvb, 2 * I, 1, kv16, H, 1, dWkv, H, split_k=_split_k(2 * I, H, Mk))
-                if dz is None:
-                    dz = _empty((Mq, H), torch.float32, dev)
-                    K.gemm_bf16(Mq, H, I, dqkv, I, 0, cfg.w16['q'], H, 1, dz, H)
-                else:
-                    K.gemm_bf16(Mq, H, I, dqkv, I, 0, cfg.w16['q'], H, 1, dz, H, accumulate=True)
-                K.gemm_bf16(Mk, H, 2 * I, dkvb, 2 * I, 0, cfg.w16['kv'], H, 1, dkv_in, H)
+                K.gemm_bf16(Mq, H, I, dqkv, I, 0, cfg.w16['q'], H, 1, dz, H, accumulate=not fresh_dz)
+                K.gemm_bf16(Mk, H, 2 * I, dkvb, 2 * I, 0, cfg.w16['vk'], H, 1, dkv_in, H)
             else:
-                dWq = _empty((I, H), torch.float32, dev)
-                dWkv = _empty((2 * I, H), torch.float32, dev)
-                K.gemm_f32(I, H, Mq, dqkv, 1, I, x, H, 1, dWq, H)
-                K.gemm_f32(2 * I, H, Mk, dkvb, 1, 2 * I, kvt, H, 1, dWkv, H)
-                acc = dz is not None
-                if dz is None:
-                    dz = _empty((Mq, H), torch.float32, dev)
-                K.gemm_f32(Mq, H, I, dq, I, 1, Wq, H, 1, dz, H, accumulate=acc)
-                K.gemm_f32(Mk, H, I, dk, 2 * I, 1, Wk, H, 1, dkv_in, H)
-                K.gemm_f32(Mk, H, I, dv, 2 * I, 1, Wv, H, 1, dkv_in, H, accumulate=True)
-            dWk, dWv = dWkv[:I], dWkv[I:]
+                K.gemm_f32(Mq, H, I, dq, I, 1, Wq, H, 1, dz, H, accumulate=not fresh_dz)
+                K.gemm_f32(Mk, H, I, dv, 2 * I, 1, Wv, H, 1, dkv_in, H)
+                K.gemm_f32(Mk, H, I, dk, 2 * I, 1, Wk, H, 1, dkv_in, H, accumulate=True)
             dkv_in = dkv_in.view(B, Nk, H)
-        return (dz.view(B, Nq, H), dkv_in, dWq, dWk, dWv, dWm, da2, db2, drel, None, dWy, dby, dWr, dbr, None)
+        g_a2 = s_a2.grads()[0] if norm else None
+        g_b2 = s_b2.grads()[0] if norm else None
+        return (dz.view(B, Nq, H), dkv_in, g_Wq, g_Wk, g_Wv, s_m.grads()[0], g_a2, g_b2, drel, None, g_Wy, g_by, g_Wr,
+                g_br, None)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -255,6 +309,7 @@ class FFNBlockFn(Function):
     @staticmethod
     def forward(ctx, x, W1, b1, W2, b2f, a2, b2, cfg):
         require_cuda(x, W1)
+        ctx.set_materialize_grads(False)
         dev = x.device
         x = x.contiguous()
         B, N, H = x.shape
@@ -279,6 +334,7 @@ class FFNBlockFn(Function):
         sigma = _empty((M,), torch.float32, dev) if norm else None
         K.ln_residual_fwd(M, H, x if cfg.residual else None, branch, a2, b2, cfg.eps, out, out16, mean, sigma, d_out)
         ctx.cfg, ctx.dims = cfg, (B, N, H, Fd)
+        ctx.small = (b1, b2f, b2)
         ctx.save_for_backward(x, W1, W2, a2, h, branch, mean, sigma, x16)
         if bf:
             ctx.mark_non_differentiable(out16)
@@ -287,9 +343,12 @@ class FFNBlockFn(Function):
 
     @staticmethod
     def backward(ctx, dout, _unused=None):
+        if dout is None:
+            return (None,) * 8
         cfg = ctx.cfg
         B, N, H, Fd = ctx.dims
         x, W1, W2, a2, h, z, mean, sigma, x16 = ctx.saved_tensors
+        b1, b2f, b2 = ctx.small
         dev = x.device
         M = B * N
         bf = cfg.precision == 'bf16'
@@ -300,40 +359,42 @@ class FFNBlockFn(Function):
         dz = _empty((M, H), torch.float32, dev) if cfg.residual else None
         separate = bf or d_out.active or not cfg.residual
         dbranch = _empty((M, H), adt, dev) if separate else None
-        da2 = torch.zeros(H, dtype=torch.float32, device=dev) if norm else None
-        db2 = torch.zeros(H, dtype=torch.float32, device=dev) if norm else None
-        K.ln_residual_bwd(M, H, dout, z, mean, sigma, a2, cfg.eps, dz, dbranch, da2, db2, d_out)
+        s_a2 = s_b2 = None
+        if norm:
+            s_a2, s_b2 = _Sink([a2], dev).prepare(True), _Sink([b2], dev).prepare(True)
+        K.ln_residual_bwd(M, H, dout, z, mean, sigma, a2, cfg.eps, dz, dbranch, s_a2.buf if norm else None,
+                          s_b2.buf if norm else None, d_out)
         if dbranch is None:
             dbranch = dz
         keep_scale = 1.0 / (1.0 - d_mid.p) if d_mid.active else 1.0
-        dbias2 = _empty((H,), torch.float32, dev)
-        dbias1 = _empty((Fd,), torch.float32, dev)
+        s_W1, s_W2, s_bias1, s_bias2 = _Sink([W1], dev), _Sink([W2], dev), _Sink([b1], dev), _Sink([b2f], dev)
         dh = _empty((M, Fd), adt, dev)
-        K.colsum(dbranch, M, H, H, dbias2)
+        s_bias2.prepare(False)
+        K.colsum(dbranch, M, H, H, s_bias2.buf, accumulate=s_bias2.direct)
+        fresh_dz = dz is None
+        if fresh_dz:
+            dz = _empty((M, H), torch.float32, dev)
         if bf:
-            dW2 = torch.zeros((H, Fd), dtype=torch.float32, device=dev)
-            dW1 = torch.zeros((Fd, H), dtype=torch.float32, device=dev)
-            K.gemm_bf16(H, Fd, M, dbranch, H, 1, h, Fd, 1, dW2, Fd, split_k=_split_k(H, Fd, M))
+            sk2, sk1 = _split_k(H, Fd, M), _split_k(Fd, H, M)
+            s_W2.prepare(zero=sk2 > 1)
+            K.gemm_bf16(H, Fd, M, dbranch, H, 1, h, Fd, 1, s_W2.buf, Fd, split_k=sk2, accumulate=s_W2.direct and sk2 == 1)
             K.gemm_bf16(M, Fd, H, dbranch, H, 0, cfg.w16['w2'], Fd, 1, dh, Fd, aux=h, ld_aux=Fd, aux_scale=keep_scale)
-            K.colsum(dh, M, Fd, Fd, dbias1)
-            K.gemm_bf16(Fd, H, M, dh, Fd, 1, x16, H, 1, dW1, H, split_k=_split_k(Fd, H, M))
-            if dz is None:
-                dz = _empty((M, H), torch.float32, dev)
-                K.gemm_bf16(M, H, Fd, dh, Fd, 0, cfg.w16['w1'], H, 1, dz, H)
-            else:
-                K.gemm_bf16(M, H, Fd, dh, Fd, 0, cfg.w16['w1'], H, 1, dz, H, accumulate=True)
+            s_bias1.prepare(False)
+            K.colsum(dh, M, Fd, Fd, s_bias1.buf, accumulate=s_bias1.direct)
+            s_W1.prepare(zero=sk1 > 1)
+            K.gemm_bf16(Fd, H, M, dh, Fd, 1, x16, H, 1, s_W1.buf, H, split_k=sk1, accumulate=s_W1.direct and sk1 == 1)
+            K.gemm_bf16(M, H, Fd, dh, Fd, 0, cfg.w16['w1'], H, 1, dz, H, accumulate=not fresh_dz)
         else:
-            dW2 = _empty((H, Fd), torch.float32, dev)
-            dW1 = _empty((Fd, H), torch.float32, dev)
-            K.gemm_f32(H, Fd, M, dbranch, 1, H, h, Fd, 1, dW2, Fd)
+            s_W2.prepare(False)
+            K.gemm_f32(H, Fd, M, dbranch, 1, H, h, Fd, 1, s_W2.buf, Fd, accumulate=s_W2.direct)
             K.gemm_f32(M, Fd, H, dbranch, H, 1, W2, Fd, 1, dh, Fd, epilogue=3, aux=h, ld_aux=Fd, aux_scale=keep_scale)
-            K.colsum(dh, M, Fd, Fd, dbias1)
-            K.gemm_f32(Fd, H, M, dh, 1, Fd, x, H, 1, dW1, H)
-            acc = dz is not None
-            if dz is None:
-                dz = _empty((M, H), torch.float32, dev)
-            K.gemm_f32(M, H, Fd, dh, Fd, 1, W1, H, 1, dz, H, accumulate=acc)
-        return dz.view(B, N, H), dW1, dbias1, dW2, dbias2, da2, db2, None
+            s_bias1.prepare(False)
+            K.colsum(dh, M, Fd, Fd, s_bias1.buf, accumulate=s_bias1.direct)
+            s_W1.prepare(False)
+            K.gemm_f32(Fd, H, M, dh, 1, Fd, x, H, 1, s_W1.buf, H, accumulate=s_W1.direct)
+            K.gemm_f32(M, H, Fd, dh, Fd, 1, W1, H, 1, dz, H, accumulate=not fresh_dz)
+        return (dz.view(B, N, H), s_W1.grads()[0], s_bias1.grads()[0], s_W2.grads()[0], s_bias2.grads()[0],
+                s_a2.grads()[0] if norm else None, s_b2.grads()[0] if norm else None, None)
 
 
 # ----------------------------------------------------------------------------------------------------------

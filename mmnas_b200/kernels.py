@@ -106,8 +106,8 @@ def cast_multi(table, n_chunks):
     call('mmnas_cast_multi', ptr(table), n_chunks, stream())
 
 
-def colsum(x, rows, cols, ld, out):
-    call('mmnas_colsum', _code(x), ptr(x), rows, cols, ld, ptr(out), stream())
+def colsum(x, rows, cols, ld, out, accumulate=False):
+    call('mmnas_colsum', _code(x), ptr(x), rows, cols, ld, ptr(out), int(accumulate), stream())
 
 
 def rng_advance(state):

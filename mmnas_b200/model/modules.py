@@ -194,10 +194,10 @@ class MHAtt(_OpBase):
         w16 = {}
         if mode == 'bf16':
             if self_att:
-                w16['qkv'] = self._fused_bf16('qkv', [self.linear_q.weight, self.linear_k.weight, self.linear_v.weight])
+                w16['vkq'] = self._fused_bf16('vkq', [self.linear_v.weight, self.linear_k.weight, self.linear_q.weight])
             else:
                 w16['q'] = self._fused_bf16('q', [self.linear_q.weight])
-                w16['kv'] = self._fused_bf16('kv', [self.linear_k.weight, self.linear_v.weight])
+                w16['vk'] = self._fused_bf16('vk', [self.linear_v.weight, self.linear_k.weight])
             w16['m'] = self._fused_bf16('m', [self.linear_merge.weight])
         cfg = BlockCfg(mode, residual, ln.eps if ln is not None else 1e-6, (d_att, d_out),
                        kmask=_key_mask(mask, B, Nk), x16=_shadow(x), kv16=None if self_att else _shadow(kv), w16=w16)
@@ -250,9 +250,9 @@ class _AttOp(nn.Module):
         """(owner module, shadow name, [weights stacked along dim 0]) for engine.WeightShadows."""
         m = self.mhatt
         if self.GUIDED:
-            specs = [(m, 'q', [m.linear_q.weight]), (m, 'kv', [m.linear_k.weight, m.linear_v.weight])]
+            specs = [(m, 'q', [m.linear_q.weight]), (m, 'vk', [m.linear_v.weight, m.linear_k.weight])]
         else:
-            specs = [(m, 'qkv', [m.linear_q.weight, m.linear_k.weight, m.linear_v.weight])]
+            specs = [(m, 'vkq', [m.linear_v.weight, m.linear_k.weight, m.linear_q.weight])]
         return specs + [(m, 'm', [m.linear_merge.weight])]
 
     def _run(self, x, kv, mask, rel_embed):

@@ -9,6 +9,8 @@ from . import kernels
 _PRECISION = 'bf16'          # 'fp32' (FFMA kernels, 1e-5 parity arm) | 'bf16' (tcgen05 arm, 2e-2)
 _rng_states = {}
 shadows_fresh = False      # True while an engine step guarantees that the managed bf16 weight shadows are current
+direct_grads = False       # True while an engine step wants block backwards to accumulate straight into p.grad
+grad_listener = None       # callable(param): the data-parallel reducer's notification for directly written grads
 _salt_counter = itertools.count(1)
 _lock = threading.Lock()
 
@@ -71,3 +73,12 @@ def advance(device=None):
     """Bump the step counter: call once per training step (captured fine inside a CUDA graph)."""
     st = rng_state(device if device is not None else torch.device('cuda', torch.cuda.current_device()))
     kernels.rng_advance(st)
+
+
+def notify_grads(params):
+    """Tell the data-parallel reducer that these parameters' gradients were written in place (no autograd hook fires
+    for a gradient a backward returns as None)."""
+    if grad_listener is not None:
+        for p in params:
+            if p is not None:
+                grad_listener(p)
