@@ -231,7 +231,9 @@ def run_b200(args):
     host_batches = [make_batch(spec, seed=1000 + 17 * rank + i) for i in range(2)]
     inputs, target = host_batches[0]
     dev_in, dev_tgt = tuple(t.to(dev) for t in inputs), target.to(dev)
-    use_graph = not args.no_graph and (world == 1 or os.environ.get('MMNAS_DP_GRAPH', '0') == '1')
+    # the whole step (incl. the bucketed NCCL all-reduces launched from the backward hooks) is one CUDA graph;
+    # MMNAS_DP_GRAPH=0 falls back to eager launches for N > 1
+    use_graph = not args.no_graph and (world == 1 or os.environ.get('MMNAS_DP_GRAPH', '1') == '1')
     step = TrainStep(net, lr_base=cfg.NET_LR_BASE, epoch_steps=10 ** 6, use_graph=use_graph)
 
     def barrier():
@@ -338,9 +340,15 @@ def run_b200(args):
                 'roofline': roofline}
         if cpu:
             line['cpu_baseline'] = cpu
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # a captured graph that contains NCCL kernels keeps the communicator busy at teardown; all results are
+        # out, so leave without the (blocking) communicator destruction
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
