@@ -29,8 +29,8 @@ BATCH = 64
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=30)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-graph', action='store_true')
@@ -118,7 +118,7 @@ def run_reference(args):
                              'sample': '%d steps at batch %d' % (args.steps, batch)},
             'e2e': {'value': val, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------ helpers
@@ -131,7 +131,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), '--query-gpu=' + self.Q,
-                                       '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.f,
+                                       '--format=csv,noheader,nounits', '-lms', '50'], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -176,9 +176,10 @@ def kernel_table(records):
             M, N, K_ = a[0], a[1], a[2]
             flops = 2.0 * M * N * K_
             byts = 2.0 * (M * K_ + N * K_) + (2.0 if a[11] else 4.0) * M * N
-            key = 'gemm_bf16[%s%s]' % ('mn' if a[5] else 'k', 'mn' if a[8] else 'k')
+            key = 'gemm_bf16_tc'        # one kernel template; MMNAS_PROFILE_SHAPES=1 splits it by layout and shape
             if os.environ.get('MMNAS_PROFILE_SHAPES'):
-                key += ' %dx%dx%d%s' % (M, N, K_, ' sk%d' % a[18] if a[18] > 1 else '')
+                key = 'gemm_bf16[%s%s] %dx%dx%d%s' % ('mn' if a[5] else 'k', 'mn' if a[8] else 'k', M, N, K_,
+                                                     ' sk%d' % a[18] if a[18] > 1 else '')
         elif name == 'mmnas_gemm_f32':
             flops = 2.0 * a[0] * a[1] * a[2]
             byts = 4.0 * (a[0] * a[2] + a[1] * a[2] + a[0] * a[1])
@@ -219,6 +220,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'INFO', 'TRACE'):
+            os.environ['NCCL_DEBUG'] = 'WARN'     # keep stdout to the single JSON line
         dist.init_process_group('nccl', device_id=dev)
     mmnas_b200.set_precision(args.precision)
     _lib.load()
@@ -307,9 +310,17 @@ def run_b200(args):
         bound, ach, peak, unit = 'tensor', top['flops'] / (top['ms'] * 1e-3) / 1e12, pk['tensor'], 'TFLOP/s'
     else:
         bound, ach, peak, unit = 'hbm', top['bytes'] / (top['ms'] * 1e-3) / 1e9, pk['hbm'], 'GB/s'
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
+        if top_name in tr:
+            traffic = tr[top_name]['dram_bytes_per_launch']
+    except (OSError, ValueError, KeyError):
+        pass
     roofline = {'kernel': top_name, 'bound': bound, 'achieved': ach, 'peak': peak, 'unit': unit, 'frac': ach / peak,
-                'traffic': None, 'peak_source': pk['src'] + (' (sustained)' if bound == 'tensor' else ''),
+                'traffic': traffic, 'peak_source': pk['src'] + (' (sustained)' if bound == 'tensor' else ''),
                 'avg_launch_ms': top['ms'] / top['launches'], 'launches_per_step': top['launches'] // n_prof,
+                'algorithmic_per_launch': (top['flops'] if bound == 'tensor' else top['bytes']) / top['launches'],
                 'share_of_kernel_time': top['ms'] / tot_ms,
                 'how': 'CUDA events around every C-ABI launch on the launching stream, %d eager steps' % n_prof}
     if args.profile_out and rank == 0:
@@ -340,7 +351,7 @@ def run_b200(args):
                 'roofline': roofline}
         if cpu:
             line['cpu_baseline'] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # a captured graph that contains NCCL kernels keeps the communicator busy at teardown; all results are
         # out, so leave without the (blocking) communicator destruction
@@ -351,7 +362,22 @@ def run_b200(args):
         os._exit(0)
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout; everything else (NCCL banners, warnings from
+    libraries writing to fd 1) was re-routed to stderr in main()."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
     args = parse()
     if args.impl == 'reference':
         run_reference(args)
