@@ -68,6 +68,37 @@ def _grad_target(params):
     return torch.as_strided(g0, shape, tuple(params[0].stride()) if params[0].dim() > 1 else (1,))
 
 
+class _Fork:
+    """Weight-gradient work of one block backward on the side stream: `with fork:` enqueues there after everything
+    issued so far on the main stream; join() makes the main stream wait for it (called before the backward returns,
+    so every buffer the side work touches is still referenced and later reuse of its memory is ordered after it).
+    Captured in a CUDA graph this becomes a parallel branch; SMs left idle by a 100-CTA dgrad GEMM run wgrad CTAs."""
+
+    def __init__(self, dev, enabled):
+        self.enabled = enabled and runtime.overlap_wgrad
+        self.used = False
+        if self.enabled:
+            self.main = torch.cuda.current_stream(dev)
+            self.side = runtime.side_stream(dev)
+            self.ctx = torch.cuda.stream(self.side)
+
+    def __enter__(self):
+        if self.enabled:
+            self.side.wait_stream(self.main)
+            self.ctx.__enter__()
+            self.used = True
+        return self
+
+    def __exit__(self, *a):
+        if self.enabled:
+            self.ctx.__exit__(*a)
+        return False
+
+    def join(self):
+        if self.enabled and self.used:
+            self.main.wait_stream(self.side)
+
+
 class _Sink:
     """Destination of a parameter gradient: the parameters' own .grad memory (direct mode: the kernel accumulates,
     autograd gets None) or a fresh buffer returned to autograd."""
@@ -205,13 +236,17 @@ class AttBlockFn(Function):
         scale = 1.0 / math.sqrt(HEAD)
         norm = a2 is not None
         dout = dout.contiguous()
+        fork = _Fork(dev, bf)
 
         def wgrad(sink, M_, N_, K_, A, lda, Bm, ldb, a32, b32):
-            """sink (+)= A^T Bm over K_ tokens.  bf16: operands [K_, M_] / [K_, N_] read MN-major; fp32: strided FFMA."""
+            """sink (+)= A^T Bm over K_ tokens.  bf16: operands [K_, M_] / [K_, N_] read MN-major; fp32: strided FFMA.
+            The sink buffer is allocated (and zeroed) on the main stream, only the GEMM may run on the side stream."""
             if bf:
                 sk = _split_k(M_, N_, K_)
                 sink.prepare(zero=sk > 1)
-                K.gemm_bf16(M_, N_, K_, A, lda, 1, Bm, ldb, 1, sink.buf, N_, split_k=sk, accumulate=sink.direct and sk == 1)
+                with fork:
+                    K.gemm_bf16(M_, N_, K_, A, lda, 1, Bm, ldb, 1, sink.buf, N_, split_k=sk,
+                                accumulate=sink.direct and sk == 1)
             else:
                 sink.prepare(zero=False)
                 K.gemm_f32(M_, N_, K_, a32, 1, lda, b32, ldb, 1, sink.buf, N_, accumulate=sink.direct)
@@ -294,6 +329,7 @@ class AttBlockFn(Function):
                 K.gemm_f32(Mk, H, I, dv, 2 * I, 1, Wv, H, 1, dkv_in, H)
                 K.gemm_f32(Mk, H, I, dk, 2 * I, 1, Wk, H, 1, dkv_in, H, accumulate=True)
             dkv_in = dkv_in.view(B, Nk, H)
+        fork.join()
         g_a2 = s_a2.grads()[0] if norm else None
         g_b2 = s_b2.grads()[0] if norm else None
         return (dz.view(B, Nq, H), dkv_in, g_Wq, g_Wk, g_Wv, s_m.grads()[0], g_a2, g_b2, drel, None, g_Wy, g_by, g_Wr,
@@ -369,22 +405,27 @@ class FFNBlockFn(Function):
         keep_scale = 1.0 / (1.0 - d_mid.p) if d_mid.active else 1.0
         s_W1, s_W2, s_bias1, s_bias2 = _Sink([W1], dev), _Sink([W2], dev), _Sink([b1], dev), _Sink([b2f], dev)
         dh = _empty((M, Fd), adt, dev)
-        s_bias2.prepare(False)
-        K.colsum(dbranch, M, H, H, s_bias2.buf, accumulate=s_bias2.direct)
+        fork = _Fork(dev, bf)
         fresh_dz = dz is None
         if fresh_dz:
             dz = _empty((M, H), torch.float32, dev)
         if bf:
             sk2, sk1 = _split_k(H, Fd, M), _split_k(Fd, H, M)
+            s_bias2.prepare(False)
             s_W2.prepare(zero=sk2 > 1)
-            K.gemm_bf16(H, Fd, M, dbranch, H, 1, h, Fd, 1, s_W2.buf, Fd, split_k=sk2, accumulate=s_W2.direct and sk2 == 1)
-            K.gemm_bf16(M, Fd, H, dbranch, H, 0, cfg.w16['w2'], Fd, 1, dh, Fd, aux=h, ld_aux=Fd, aux_scale=keep_scale)
             s_bias1.prepare(False)
-            K.colsum(dh, M, Fd, Fd, s_bias1.buf, accumulate=s_bias1.direct)
             s_W1.prepare(zero=sk1 > 1)
-            K.gemm_bf16(Fd, H, M, dh, Fd, 1, x16, H, 1, s_W1.buf, H, split_k=sk1, accumulate=s_W1.direct and sk1 == 1)
+            with fork:       # db2, dW2 need only dbranch: they overlap the dh GEMM
+                K.colsum(dbranch, M, H, H, s_bias2.buf, accumulate=s_bias2.direct)
+                K.gemm_bf16(H, Fd, M, dbranch, H, 1, h, Fd, 1, s_W2.buf, Fd, split_k=sk2, accumulate=s_W2.direct and sk2 == 1)
+            K.gemm_bf16(M, Fd, H, dbranch, H, 0, cfg.w16['w2'], Fd, 1, dh, Fd, aux=h, ld_aux=Fd, aux_scale=keep_scale)
+            with fork:       # db1, dW1 need dh: they overlap the dx GEMM
+                K.colsum(dh, M, Fd, Fd, s_bias1.buf, accumulate=s_bias1.direct)
+                K.gemm_bf16(Fd, H, M, dh, Fd, 1, x16, H, 1, s_W1.buf, H, split_k=sk1, accumulate=s_W1.direct and sk1 == 1)
             K.gemm_bf16(M, H, Fd, dh, Fd, 0, cfg.w16['w1'], H, 1, dz, H, accumulate=not fresh_dz)
         else:
+            s_bias2.prepare(False)
+            K.colsum(dbranch, M, H, H, s_bias2.buf, accumulate=s_bias2.direct)
             s_W2.prepare(False)
             K.gemm_f32(H, Fd, M, dbranch, 1, H, h, Fd, 1, s_W2.buf, Fd, accumulate=s_W2.direct)
             K.gemm_f32(M, Fd, H, dbranch, H, 1, W2, Fd, 1, dh, Fd, epilogue=3, aux=h, ld_aux=Fd, aux_scale=keep_scale)
@@ -393,6 +434,7 @@ class FFNBlockFn(Function):
             s_W1.prepare(False)
             K.gemm_f32(Fd, H, M, dh, 1, Fd, x, H, 1, s_W1.buf, H, accumulate=s_W1.direct)
             K.gemm_f32(M, H, Fd, dh, Fd, 1, W1, H, 1, dz, H, accumulate=not fresh_dz)
+        fork.join()
         return (dz.view(B, N, H), s_W1.grads()[0], s_bias1.grads()[0], s_W2.grads()[0], s_bias2.grads()[0],
                 s_a2.grads()[0] if norm else None, s_b2.grads()[0] if norm else None, None)
 

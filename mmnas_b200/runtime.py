@@ -10,6 +10,7 @@ _PRECISION = 'bf16'          # 'fp32' (FFMA kernels, 1e-5 parity arm) | 'bf16' (
 _rng_states = {}
 shadows_fresh = False      # True while an engine step guarantees that the managed bf16 weight shadows are current
 direct_grads = False       # True while an engine step wants block backwards to accumulate straight into p.grad
+overlap_wgrad = True       # run weight-gradient GEMMs on a side stream, concurrently with the dgrad / attention chain
 grad_listener = None       # callable(param): the data-parallel reducer's notification for directly written grads
 _salt_counter = itertools.count(1)
 _lock = threading.Lock()
@@ -82,3 +83,16 @@ def notify_grads(params):
         for p in params:
             if p is not None:
                 grad_listener(p)
+
+
+_side_streams = {}
+
+
+def side_stream(device):
+    """The per-device side stream for work that is independent of the main backward chain (weight gradients)."""
+    key = torch.device(device)
+    st = _side_streams.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=key)
+        _side_streams[key] = st
+    return st
