@@ -1,7 +1,7 @@
 // Attention core on the 5th-gen tensor cores (bf16 arm).  One CTA (128 threads) per (sample, head):
 //   forward   S = Q K^T          (tcgen05.mma 128 x N1 x 64, accumulator in TMEM columns [0,128))
 //             softmax: thread i owns query row i == TMEM lane i, so row max / sum are thread-local (no shuffles);
-//             logits are read twice from TMEM (max pass, exp pass) instead of living in 128 registers
+//             the whole row of logits stays in registers (TMEM is read once)
 //             P (bf16, dropout applied) -> shared memory in the canonical K-major 128B-swizzled UMMA layout
 //             O = P V            (A = P K-major, B = V as an MN-major operand straight from its TMA tile)
 //   backward  S = Q K^T, dP = dO V^T                       (V's tile re-read as a K-major operand)
@@ -237,25 +237,26 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
 }
 
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128, 2)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                    const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo, AttnTcArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t sQ = smem_u32(smem), sK = sQ + TILE_BYTES, sV = sK + TILE_BYTES, sdO = sV + TILE_BYTES;
-  const uint32_t sP = sdO + TILE_BYTES, sdS = sP + PTILE_BYTES;
-  uint8_t* gP = smem + 4 * TILE_BYTES;
+  // Two CTAs per SM: 112 KB of shared memory and 256 TMEM columns each.
+  //   smem: Q | K | dO | P chunk 0 | V (= P chunk 1 once dP = dO V^T has retired) | dS chunk 0 | dS chunk 1
+  //   TMEM: phase 1  S [0,128)  dP [128,256);  phase 2 (S, dP consumed)  dQ [0,64)  dK [64,128)  dV [128,192)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sQ = smem_u32(smem), sK = sQ + TILE_BYTES, sdO = sK + TILE_BYTES, sP = sdO + TILE_BYTES;
+  const uint32_t sV = sP + TILE_BYTES, sdS = sV + TILE_BYTES;
+  uint8_t* gP = smem + 3 * TILE_BYTES;
   uint8_t* gdS = gP + PTILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 4 * TILE_BYTES + 2 * PTILE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * TILE_BYTES + 2 * PTILE_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   const uint32_t bar = smem_u32(bars);
   const int h = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int Nq = a.Nq, Nk = a.Nk;
-  tc_prologue(bar, 3, tmem_slot, 512, warp);
+  tc_prologue(bar, 3, tmem_slot, 256, warp);
   pdl_wait();
   const uint32_t tmem = *tmem_slot;
-  // TMEM columns: S [0,128) dP [128,256) dQ [256,320) dK [320,384) dV [384,448)
   const int n1 = max(16, (Nk + 15) & ~15);
   if (tid == 0) {
     mbar_expect_tx(bar, 4 * TILE_BYTES);
@@ -372,14 +373,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     // dQ = dS K : A = dS K-major (k = j), B = K tile as MN-major (k-rows j, n = head column)
     const uint32_t id_q = make_idesc(false, true, 128, 64);
     for (int t = 0; t < ksteps_j; ++t)
-      umma_bf16(tmem + 256, make_smem_desc(sdS + (t >> 2) * TILE_BYTES + (t & 3) * 32, 16, 1024),
+      umma_bf16(tmem + 0, make_smem_desc(sdS + (t >> 2) * TILE_BYTES + (t & 3) * 32, 16, 1024),
                 make_smem_desc(sK + t * 2048, 8192, 1024), id_q, t > 0);
     // dK = dS^T Q, dV = Pd^T dO : A = the same [i][j] tiles read MN-major (m = j: two 64-wide chunks, k-rows = i)
     const uint32_t id_t = make_idesc(true, true, 128, 64);
     for (int t = 0; t < ksteps_i; ++t)
-      umma_bf16(tmem + 320, make_smem_desc(sdS + t * 2048, TILE_BYTES, 1024), make_smem_desc(sQ + t * 2048, 8192, 1024), id_t, t > 0);
+      umma_bf16(tmem + 64, make_smem_desc(sdS + t * 2048, TILE_BYTES, 1024), make_smem_desc(sQ + t * 2048, 8192, 1024), id_t, t > 0);
     for (int t = 0; t < ksteps_i; ++t)
-      umma_bf16(tmem + 384, make_smem_desc(sP + t * 2048, TILE_BYTES, 1024), make_smem_desc(sdO + t * 2048, 8192, 1024), id_t, t > 0);
+      umma_bf16(tmem + 128, make_smem_desc(sP + t * 2048, TILE_BYTES, 1024), make_smem_desc(sdO + t * 2048, 8192, 1024), id_t, t > 0);
     umma_commit(bar + 16);
   }
   mbar_wait(bar + 16, 0);
@@ -396,7 +397,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
 #pragma unroll
     for (int cc = 0; cc < 2; ++cc) {
       uint32_t r[32];
-      tmem_ld32(trow + 256 + which * 64 + cc * 32, r);
+      tmem_ld32(trow + which * 64 + cc * 32, r);
       if (ok) {
         __nv_bfloat16* row = base + h * 64 + cc * 32;
 #pragma unroll
@@ -412,11 +413,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
 }
 
 constexpr int FWD_SMEM = 3 * TILE_BYTES + PTILE_BYTES + 1024 + 128;
-constexpr int BWD_SMEM = 4 * TILE_BYTES + 2 * PTILE_BYTES + 1024 + 128;
+constexpr int BWD_SMEM = 3 * TILE_BYTES + 2 * PTILE_BYTES + 128;
 
 DropCfg mk_drop(const unsigned long long* st, unsigned long long salt, float p) {
   DropCfg d;
