@@ -34,21 +34,21 @@ class FlatGrads:
             self.offsets.append(off)
             off += (p.numel() + 3) // 4 * 4          # keep every view 16-byte aligned
         self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.views = [self.flat[o:o + p.numel()].view_as(p) for o, p in zip(self.offsets, self.params)]
         self.install()
 
     def view(self, i):
-        p = self.params[i]
-        return self.flat[self.offsets[i]:self.offsets[i] + p.numel()].view_as(p)
+        return self.views[i]
 
     def install(self):
-        for i, p in enumerate(self.params):
-            p.grad = self.view(i)
+        for p, v in zip(self.params, self.views):
+            p.grad = v
 
     def zero(self):
         self.flat.zero_()
-        for i, p in enumerate(self.params):         # MixedOp.binarize() sets candidate grads to None
-            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + 4 * self.offsets[i]:
-                p.grad = self.view(i)
+        for p, v in zip(self.params, self.views):   # MixedOp.binarize() sets candidate grads to None
+            if p.grad is not v:
+                p.grad = v
 
 
 class BucketReducer:
@@ -304,23 +304,28 @@ class SearchStep:
         self.optim = WarmupAdam(self.net_params, lr_base, epoch_steps)
         self.alpha_optim = torch.optim.Adam(list(net.alpha_prob_parameters()), alpha_lr, betas=alpha_betas,
                                             weight_decay=0)
+        self.shadows = WeightShadows(net)       # every candidate's GEMM weights, one batched cast per step
 
     def _forward_backward(self, inputs, target):
         self.grads.zero()                # net.zero_grad() + the reference's 0*sum(params) dummy terms
         self.reducer.reset()
         runtime.advance(target.device)
+        if runtime.get_precision() == 'bf16':
+            self.shadows.refresh()
+            runtime.shadows_fresh = True
         runtime.direct_grads, runtime.grad_listener = True, self.reducer.notify
         try:
             loss = self.loss_fn(self.net(inputs), target)
             loss.backward()
         finally:
+            runtime.shadows_fresh = False
             runtime.direct_grads, runtime.grad_listener = False, None
         self.reducer.finish()
         return loss.detach()
 
     def weight_step(self, inputs, target):
         MixedOp.MODE = None
-        self.net.reset_binary_gates()
+        self.net.reset_binary_gates(batched=True)
         self.net.unused_modules_off()
         try:
             self.optim.set_lr()
@@ -332,7 +337,7 @@ class SearchStep:
 
     def arch_step(self, inputs, target):
         MixedOp.MODE = self.mode
-        self.net.reset_binary_gates()
+        self.net.reset_binary_gates(batched=(self.mode != 'two'))
         self.net.unused_modules_off()
         try:
             loss = self._forward_backward(inputs, target)

@@ -199,9 +199,28 @@ class Net_Search(_NetBase):
             self._redundant_modules = [m for m in self.modules() if str(m).startswith('MixedOp')]
         return self._redundant_modules
 
-    def reset_binary_gates(self):
+    def reset_binary_gates(self, batched=False):
+        """Sample every node's active path (MixedOp.binarize, mixed.py:131-163).  batched=True draws all nodes of
+        equal width with ONE multinomial call and ONE host read (2 syncs per step instead of 30) and leaves the
+        candidates' .grad buffers alone — the step harness zeroes the flat gradient buffer, which is what the
+        reference's dummy-loss terms turn the None grads into anyway.  Not for MODE 'two'."""
+        if not batched:
+            for m in self.redundant_modules:
+                m.binarize()
+            return
+        groups = {}
         for m in self.redundant_modules:
-            m.binarize()
+            groups.setdefault(m.n_choices, []).append(m)
+        with torch.no_grad():
+            for k, mods in groups.items():
+                probs = F.softmax(torch.stack([m.alpha_prob.data for m in mods]), dim=1)
+                picks = torch.multinomial(probs, 1).squeeze(1)
+                onehot = F.one_hot(picks, k).to(probs.dtype)
+                idx = picks.tolist()
+                for m, a, g in zip(mods, idx, onehot):
+                    m.alpha_gate.data.copy_(g)
+                    m.active_index = [a]
+                    m.inactive_index = [i for i in range(k) if i != a]
 
     def unused_modules_off(self):
         self._unused_modules = []
