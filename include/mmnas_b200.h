@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MMNAS_B200_ABI_VERSION 2
+#define MMNAS_B200_ABI_VERSION 3
 
 typedef void* mmnas_stream;
 
@@ -101,6 +101,16 @@ int mmnas_cast_f32_to_bf16(const float* src, void* dst, long n, mmnas_stream str
 int mmnas_cast_multi(const void* table, int n_chunks, mmnas_stream stream);
 /* out[c] (+)= sum_r x[r,c] (bias gradients); accumulate == 0 overwrites out, 1 adds into it (gradient buffers). */
 int mmnas_colsum(int dtype, const void* x, int rows, int cols, long ld, float* out, int accumulate, mmnas_stream stream);
+/* ---- optimizer tail: clip_grad_norm_ (train_vqa.py:310) + Adam (train_vqa.py:311 via optimizer.py:14-20) ------
+ * out[0] = sum(x^2) over a flat fp32 buffer (n % 4 == 0). */
+int mmnas_sumsq_f32(const float* x, long n, float* out, mmnas_stream stream);
+/* One launch updates every parameter: `table` = DEVICE array of n_chunks rows of 5 int64 {param*, grad*, exp_avg*,
+ * exp_avg_sq*, count} (count <= 4096).  Gradients are scaled by min(1, max_norm / (sqrt(*sumsq) + 1e-6))
+ * (max_norm <= 0: no clipping); lr is read from device memory, the step count t from step_state[1] (advance it with
+ * mmnas_rng_advance before the call), so the call can be replayed from a CUDA graph. */
+int mmnas_clip_adam(const void* table, int n_chunks, const float* sumsq, const float* lr,
+                    const unsigned long long* step_state, float beta1, float beta2, float eps, float max_norm,
+                    mmnas_stream stream);
 /* state[1] += 1: call once per training step so every step draws fresh dropout masks (graph-capturable). */
 int mmnas_rng_advance(unsigned long long* state, mmnas_stream stream);
 

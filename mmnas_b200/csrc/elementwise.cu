@@ -158,6 +158,72 @@ __global__ void __launch_bounds__(EW_THREADS) cast_multi_kernel(const long long*
   }
 }
 
+// ---- optimizer tail: clip_grad_norm_ + Adam in two passes over flat / tabled buffers ----------
+__global__ void __launch_bounds__(EW_THREADS) sumsq_kernel(const float* __restrict__ x, long n, float* __restrict__ out) {
+  __shared__ float red[EW_THREADS / 32];
+  pdl_wait(); pdl_launch();
+  float s = 0.f;
+  const long nvec = n >> 2;
+  for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (long)gridDim.x * blockDim.x) {
+    const float4 f = *reinterpret_cast<const float4*>(x + 4 * v);
+    s += (f.x * f.x + f.y * f.y) + (f.z * f.z + f.w * f.w);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < EW_THREADS / 32; ++w) t += red[w];
+    atomicAdd(out, t);
+  }
+}
+
+// table[c] = {param*, grad*, exp_avg*, exp_avg_sq*, count (<= 4096)}.  torch.optim.Adam arithmetic
+// (no amsgrad, no weight decay): p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps), with the gradient first
+// scaled by clip_grad_norm_'s coefficient min(1, max_norm / (||g|| + 1e-6)).
+__global__ void __launch_bounds__(EW_THREADS) clip_adam_kernel(const long long* __restrict__ table, const float* __restrict__ sumsq,
+                                                               const float* __restrict__ lr_ptr, const unsigned long long* __restrict__ step_state,
+                                                               float b1, float b2, float eps, float max_norm) {
+  pdl_wait(); pdl_launch();
+  const long long* e = table + 5 * (long long)blockIdx.x;
+  float* p = reinterpret_cast<float*>(e[0]);
+  const float* g = reinterpret_cast<const float*>(e[1]);
+  float* m = reinterpret_cast<float*>(e[2]);
+  float* v = reinterpret_cast<float*>(e[3]);
+  const int count = (int)e[4];
+  const bool aligned = (((e[0] | e[1] | e[2] | e[3]) & 15) == 0);
+  const int nvec = aligned ? (count >> 2) : 0;
+  float coef = 1.f;
+  if (max_norm > 0.f) coef = fminf(1.f, max_norm / (sqrtf(*sumsq) + 1e-6f));
+  const float t = (float)step_state[1];
+  const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+  const float step_size = *lr_ptr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  for (int i = threadIdx.x; i < nvec; i += EW_THREADS) {
+    float4 gv = *reinterpret_cast<const float4*>(g + 4 * i);
+    float4 mv = *reinterpret_cast<const float4*>(m + 4 * i);
+    float4 vv = *reinterpret_cast<const float4*>(v + 4 * i);
+    float4 pv = *reinterpret_cast<const float4*>(p + 4 * i);
+    float gg[4] = {gv.x * coef, gv.y * coef, gv.z * coef, gv.w * coef};
+    float mm[4] = {mv.x, mv.y, mv.z, mv.w}, vq[4] = {vv.x, vv.y, vv.z, vv.w}, pp[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      mm[u] = b1 * mm[u] + (1.f - b1) * gg[u];
+      vq[u] = b2 * vq[u] + (1.f - b2) * gg[u] * gg[u];
+      pp[u] -= step_size * mm[u] / (sqrtf(vq[u]) * inv_sqrt_bc2 + eps);
+    }
+    *reinterpret_cast<float4*>(m + 4 * i) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    *reinterpret_cast<float4*>(v + 4 * i) = make_float4(vq[0], vq[1], vq[2], vq[3]);
+    *reinterpret_cast<float4*>(p + 4 * i) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+  }
+  for (int i = 4 * nvec + threadIdx.x; i < count; i += EW_THREADS) {     // unaligned tensors and tails
+    const float gg = g[i] * coef;
+    const float mm = b1 * m[i] + (1.f - b1) * gg;
+    const float vq = b2 * v[i] + (1.f - b2) * gg * gg;
+    m[i] = mm; v[i] = vq;
+    p[i] -= step_size * mm / (sqrtf(vq) * inv_sqrt_bc2 + eps);
+  }
+}
+
 __global__ void rng_advance_kernel(unsigned long long* state) { state[1] += 1ull; }
 
 }  // namespace
@@ -224,6 +290,26 @@ extern "C" int mmnas_mixed_alpha_dot(int K, const float* const* outs, const floa
     a.d_o[k] = d_outs ? d_outs[k] : nullptr;
   }
   MMNAS_CUDA(mmnas_launch(mixed_alpha_dot_kernel, dim3(ew_grid(n >> 2)), dim3(EW_THREADS), 0, s, a));
+  return MMNAS_OK;
+}
+
+extern "C" int mmnas_sumsq_f32(const float* x, long n, float* out, mmnas_stream stream) {
+  MMNAS_CHECK_ARG(x && out && n >= 0 && (n % 4) == 0 && ((uintptr_t)x % 16) == 0, "sumsq: bad argument (n % 4, 16-byte alignment)");
+  cudaStream_t s = (cudaStream_t)stream;
+  MMNAS_CUDA(cudaMemsetAsync(out, 0, sizeof(float), s));
+  if (n == 0) return MMNAS_OK;
+  MMNAS_CUDA(mmnas_launch(sumsq_kernel, dim3(ew_grid(n >> 2)), dim3(EW_THREADS), 0, s, x, n, out));
+  return MMNAS_OK;
+}
+
+extern "C" int mmnas_clip_adam(const void* table, int n_chunks, const float* sumsq, const float* lr,
+                               const unsigned long long* step_state, float beta1, float beta2, float eps, float max_norm,
+                               mmnas_stream stream) {
+  MMNAS_CHECK_ARG(n_chunks >= 0, "clip_adam: negative chunk count");
+  if (n_chunks == 0) return MMNAS_OK;
+  MMNAS_CHECK_ARG(table && lr && step_state && (max_norm <= 0.f || sumsq), "clip_adam: null argument");
+  MMNAS_CUDA(mmnas_launch(clip_adam_kernel, dim3(n_chunks), dim3(EW_THREADS), 0, (cudaStream_t)stream,
+                          (const long long*)table, sumsq, lr, step_state, beta1, beta2, eps, max_norm));
   return MMNAS_OK;
 }
 

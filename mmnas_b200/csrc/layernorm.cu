@@ -253,7 +253,7 @@ extern "C" int mmnas_ln_residual_bwd(int rows, int H, const float* dout, const f
   DropCfg d = make_drop(rng_state, salt, p);
   size_t smem = gamma ? 2 * (size_t)H * sizeof(float) : 0;
   int ctas = ceil_div(rows, ROWS_PER_CTA);
-  if (ctas > 148 * 4) ctas = 148 * 4;   // grid-stride over rows: column partials stay in registers
+  if (ctas > 148 * 2) ctas = 148 * 2;   // one resident wave (2 CTAs/SM at ~120 registers); rows are grid-strided
   dim3 grid(ctas), block(ROWS_PER_CTA * 32);
   cudaStream_t s = (cudaStream_t)stream;
 #define LN_BWD(TB, NV, EX) MMNAS_CUDA(mmnas_launch(ln_bwd_kernel<TB, NV, EX>, grid, block, smem, s, rows, H, dout, z, mean, sigma, gamma, eps, dz, (TB*)dbranch, dgamma, dbeta, d))

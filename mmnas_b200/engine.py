@@ -178,12 +178,18 @@ class WarmupAdam:
     """Adam(lr schedule of WarmupOptimizer, optimizer.py:14-47) preceded by clip_grad_norm_ (train_vqa.py:309-311)."""
 
     def __init__(self, params, lr_base, epoch_steps, betas=(0.9, 0.98), eps=1e-9, clip=1.0, warmup=True,
-                 capturable=False):
+                 capturable=False, flat_grads=None):
         self.params = [p for p in params if p.requires_grad]
         self.lr_base, self.epoch_steps, self.warmup, self.clip = lr_base, max(1, epoch_steps), warmup, clip
         self._step = 0
         self._rate = 0.0
         self.capturable = capturable
+        self.fused = None
+        if flat_grads is not None and self.params[0].is_cuda:
+            # clip + Adam as two CUDA passes over the flat gradient buffer (mmnas_sumsq_f32 + mmnas_clip_adam)
+            self.fused = FusedClipAdam(flat_grads, self.params, betas, eps, clip)
+            self.optimizer = None
+            return
         lr = torch.tensor(0.0, device=self.params[0].device) if capturable else 0.0
         self.optimizer = torch.optim.Adam(self.params, lr=lr, betas=betas, eps=eps, weight_decay=0,
                                           fused=self.params[0].is_cuda, capturable=capturable)
@@ -204,6 +210,9 @@ class WarmupAdam:
         """Host side of a step: advance the schedule and publish the learning rate."""
         self._step += 1
         self._rate = self.rate()
+        if self.fused is not None:
+            self.fused.lr.fill_(self._rate)
+            return
         for g in self.optimizer.param_groups:
             if torch.is_tensor(g['lr']):
                 g['lr'].fill_(self._rate)
@@ -211,9 +220,57 @@ class WarmupAdam:
                 g['lr'] = self._rate
 
     def clip_and_step(self):
+        if self.fused is not None:
+            self.fused.step()
+            return
         if self.clip and self.clip > 0:
             torch.nn.utils.clip_grad_norm_(self.params, self.clip, foreach=True)
         self.optimizer.step()
+
+
+class FusedClipAdam:
+    """clip_grad_norm_(max_norm) + Adam over the parameters `params`, whose gradients are a CONTIGUOUS prefix range of
+    a FlatGrads buffer: one reduction pass over the flat gradients, one tabled update pass over (param, grad, m, v).
+    Learning rate and step count live on the device, so the step replays from a CUDA graph."""
+    CHUNK = 4096
+
+    def __init__(self, flat_grads, params, betas, eps, clip):
+        from . import kernels
+        self.kernels = kernels
+        fg = flat_grads
+        wanted = {id(q) for q in params}
+        idx = [i for i, p in enumerate(fg.params) if id(p) in wanted]
+        assert idx == list(range(idx[0], idx[0] + len(idx))), 'parameters must be contiguous in the flat gradient buffer'
+        first, last = idx[0], idx[-1]
+        self.lo = fg.offsets[first]
+        self.hi = fg.offsets[last] + (fg.params[last].numel() + 3) // 4 * 4
+        dev = fg.flat.device
+        self.grad_range = fg.flat[self.lo:self.hi]
+        self.exp_avg = torch.zeros(self.hi - self.lo, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(self.hi - self.lo, dtype=torch.float32, device=dev)
+        self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.lr = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.state = torch.zeros(2, dtype=torch.int64, device=dev)        # [unused, step count]
+        self.betas, self.eps, self.clip = betas, eps, (clip if clip else 0.0)
+        rows = []
+        for i in idx:
+            p = fg.params[i]
+            off = fg.offsets[i] - self.lo
+            g_ptr = fg.flat.data_ptr() + 4 * fg.offsets[i]
+            for c in range(0, p.numel(), self.CHUNK):
+                rows.append((p.data_ptr() + 4 * c, g_ptr + 4 * c, self.exp_avg.data_ptr() + 4 * (off + c),
+                             self.exp_avg_sq.data_ptr() + 4 * (off + c), min(self.CHUNK, p.numel() - c)))
+            assert p.is_contiguous()
+        self.n_chunks = len(rows)
+        self.table = torch.tensor(rows, dtype=torch.int64, device=dev)
+
+    def step(self):
+        k = self.kernels
+        k.rng_advance(self.state)
+        if self.clip > 0:
+            k.sumsq(self.grad_range, self.sumsq)
+        k.clip_adam(self.table, self.n_chunks, self.sumsq, self.lr, self.state, self.betas[0], self.betas[1], self.eps,
+                    float(self.clip))
 
 
 # ------------------------------------------------------------------------------------------------ steps
@@ -232,7 +289,8 @@ class TrainStep:
         self.reducer = BucketReducer(self.grads, bucket_mb=bucket_mb)
         # NCCL all-reduces launched from the backward hooks are captured with the rest of the step
         self.use_graph = use_graph
-        self.optim = WarmupAdam(self.grads.params, lr_base, epoch_steps, betas, eps, clip, capturable=self.use_graph)
+        self.optim = WarmupAdam(self.grads.params, lr_base, epoch_steps, betas, eps, clip, capturable=self.use_graph,
+                                flat_grads=self.grads)
         self.shadows = WeightShadows(net)
         self.graph = None
         self._static_in = self._static_tgt = self._static_loss = None
@@ -298,10 +356,11 @@ class SearchStep:
         self.net = net
         self.mode = mode
         self.loss_fn = loss_fn
-        self.grads = FlatGrads(net.parameters())          # weights, alpha_prob and alpha_gate
-        self.reducer = BucketReducer(self.grads, bucket_mb=bucket_mb)
         self.net_params = [p for p in net.net_parameters()]
-        self.optim = WarmupAdam(self.net_params, lr_base, epoch_steps)
+        alphas = list(net.alpha_prob_parameters()) + list(net.alpha_gate_parameters())
+        self.grads = FlatGrads(self.net_params + alphas)  # weights first (a contiguous range for clip + Adam), then alphas
+        self.reducer = BucketReducer(self.grads, bucket_mb=bucket_mb)
+        self.optim = WarmupAdam(self.net_params, lr_base, epoch_steps, flat_grads=self.grads)
         self.alpha_optim = torch.optim.Adam(list(net.alpha_prob_parameters()), alpha_lr, betas=alpha_betas,
                                             weight_decay=0)
         self.shadows = WeightShadows(net)       # every candidate's GEMM weights, one batched cast per step

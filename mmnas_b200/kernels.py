@@ -110,5 +110,14 @@ def colsum(x, rows, cols, ld, out, accumulate=False):
     call('mmnas_colsum', _code(x), ptr(x), rows, cols, ld, ptr(out), int(accumulate), stream())
 
 
+def sumsq(flat, out):
+    call('mmnas_sumsq_f32', ptr(flat), flat.numel(), ptr(out), stream())
+
+
+def clip_adam(table, n_chunks, sumsq_buf, lr, step_state, beta1, beta2, eps, max_norm):
+    call('mmnas_clip_adam', ptr(table), n_chunks, ptr(sumsq_buf), ptr(lr), ptr(step_state), beta1, beta2, eps, max_norm,
+         stream())
+
+
 def rng_advance(state):
     call('mmnas_rng_advance', ptr(state), stream())

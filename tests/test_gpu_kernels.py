@@ -320,3 +320,32 @@ def test_bad_arguments_raise():
         k.attn_fwd(1, 1, 8, 8, q.data_ptr(), 32, q.data_ptr(), 32, q.data_ptr(), 32, None, None, o, 32, 0.1, head_dim=32)
     with pytest.raises(MMnasLibraryError):
         k.gemm_bf16(8, 30, 8, q.bfloat16(), 8, 0, q.bfloat16(), 8, 0, o, 30)   # N % 32 != 0
+
+
+def test_fused_clip_adam_matches_torch():
+    """mmnas_sumsq_f32 + mmnas_clip_adam against clip_grad_norm_(1.0) + torch.optim.Adam(betas=(.9,.98), eps=1e-9) — the
+    step tail of train_vqa.py:309-311 — over 5 steps, incl. an odd-sized tensor (tail path) and a tiny one."""
+    from mmnas_b200.engine import FlatGrads, WarmupAdam
+    torch.manual_seed(0)
+    shapes = [(512, 512), (3129,), (2048, 512), (7,), (64, 4)]
+    ps_a = [torch.nn.Parameter(torch.randn(*s, device=DEV)) for s in shapes]
+    ps_b = [torch.nn.Parameter(p.detach().clone()) for p in ps_a]
+    fg = FlatGrads(ps_a)
+    fused = WarmupAdam(ps_a, lr_base=1e-2, epoch_steps=2, flat_grads=fg)
+    assert fused.fused is not None
+    ref = torch.optim.Adam(ps_b, lr=0.0, betas=(0.9, 0.98), eps=1e-9)
+    for step in range(5):
+        fg.zero()
+        gs = [torch.randn(*s, device=DEV) * (3.0 if step % 2 else 0.01) for s in shapes]   # clipped / not clipped
+        for p, q, g in zip(ps_a, ps_b, gs):
+            p.grad.copy_(g)
+            q.grad = g.clone()
+        fused.set_lr()
+        fused.clip_and_step()
+        torch.nn.utils.clip_grad_norm_(ps_b, 1.0)
+        for grp in ref.param_groups:
+            grp['lr'] = fused._rate
+        ref.step()
+    for p, q in zip(ps_a, ps_b):
+        assert normwise(p, q) < 2e-6
+    assert abs(fused._rate - 1e-2) < 1e-12 and fused.rate(1) == 2.5e-3
