@@ -348,4 +348,4 @@ def test_fused_clip_adam_matches_torch():
         ref.step()
     for p, q in zip(ps_a, ps_b):
         assert normwise(p, q) < 2e-6
-    assert abs(fused._rate - 1e-2) < 1e-12 and fused.rate(1) == 2.5e-3
+    assert abs(fused._rate - 0.75e-2) < 1e-12 and fused.rate(1) == 2.5e-3      # step 5 of 2-step 'epochs': 3/4 warm-up
