@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MMNAS_B200_ABI_VERSION 3
+#define MMNAS_B200_ABI_VERSION 4
 
 typedef void* mmnas_stream;
 
@@ -101,6 +101,10 @@ int mmnas_cast_f32_to_bf16(const float* src, void* dst, long n, mmnas_stream str
 int mmnas_cast_multi(const void* table, int n_chunks, mmnas_stream stream);
 /* out[c] (+)= sum_r x[r,c] (bias gradients); accumulate == 0 overwrites out, 1 adds into it (gradient buffers). */
 int mmnas_colsum(int dtype, const void* x, int rows, int cols, long ld, float* out, int accumulate, mmnas_stream stream);
+/* ---- stem: bf16 copy of the region features (optional, NULL to skip) + make_mask() (full_vqa.py:113-114):
+ * mask[r] = 1 iff every element of row r is zero (== sum|x| == 0). */
+int mmnas_cast_rowmask(const float* x, void* x_bf16, unsigned char* mask, int rows, int cols, mmnas_stream stream);
+
 /* ---- optimizer tail: clip_grad_norm_ (train_vqa.py:310) + Adam (train_vqa.py:311 via optimizer.py:14-20) ------
  * out[0] = sum(x^2) over a flat fp32 buffer (n % 4 == 0). */
 int mmnas_sumsq_f32(const float* x, long n, float* out, mmnas_stream stream);

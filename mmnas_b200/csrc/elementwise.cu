@@ -158,6 +158,33 @@ __global__ void __launch_bounds__(EW_THREADS) cast_multi_kernel(const long long*
   }
 }
 
+// ---- stem: one pass over the region features gives their bf16 copy (A operand of the image
+// projection GEMM) and the padding mask make_mask() derives from them (full_vqa.py:113-114: sum|x| == 0) -----------
+__global__ void __launch_bounds__(EW_THREADS) cast_rowmask_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ x16,
+                                                                  unsigned char* __restrict__ mask, int cols) {
+  __shared__ int any_nz;
+  pdl_wait(); pdl_launch();
+  if (threadIdx.x == 0) any_nz = 0;
+  __syncthreads();
+  const long base = (long)blockIdx.x * cols;
+  const int nvec = cols >> 2;
+  bool nz = false;
+  for (int v = threadIdx.x; v < nvec; v += EW_THREADS) {
+    const float4 f = *reinterpret_cast<const float4*>(x + base + 4 * v);
+    nz |= (f.x != 0.f) | (f.y != 0.f) | (f.z != 0.f) | (f.w != 0.f);
+    if (x16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(f.x, f.y), hi = __floats2bfloat162_rn(f.z, f.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<unsigned*>(&lo);
+      pk.y = *reinterpret_cast<unsigned*>(&hi);
+      *reinterpret_cast<uint2*>(x16 + base + 4 * v) = pk;
+    }
+  }
+  if (__any_sync(0xffffffffu, nz) && (threadIdx.x & 31) == 0) atomicOr(&any_nz, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) mask[blockIdx.x] = any_nz ? 0 : 1;
+}
+
 // ---- optimizer tail: clip_grad_norm_ + Adam in two passes over flat / tabled buffers ----------
 __global__ void __launch_bounds__(EW_THREADS) sumsq_kernel(const float* __restrict__ x, long n, float* __restrict__ out) {
   __shared__ float red[EW_THREADS / 32];
@@ -290,6 +317,14 @@ extern "C" int mmnas_mixed_alpha_dot(int K, const float* const* outs, const floa
     a.d_o[k] = d_outs ? d_outs[k] : nullptr;
   }
   MMNAS_CUDA(mmnas_launch(mixed_alpha_dot_kernel, dim3(ew_grid(n >> 2)), dim3(EW_THREADS), 0, s, a));
+  return MMNAS_OK;
+}
+
+extern "C" int mmnas_cast_rowmask(const float* x, void* x_bf16, unsigned char* mask, int rows, int cols, mmnas_stream stream) {
+  MMNAS_CHECK_ARG(rows >= 0 && cols > 0 && (cols % 4) == 0, "cast_rowmask: cols must be a multiple of 4");
+  if (rows == 0) return MMNAS_OK;
+  MMNAS_CHECK_ARG(x && mask && ((uintptr_t)x % 16) == 0 && ((uintptr_t)x_bf16 % 8) == 0, "cast_rowmask: null / misaligned buffer");
+  MMNAS_CUDA(mmnas_launch(cast_rowmask_kernel, dim3(rows), dim3(EW_THREADS), 0, (cudaStream_t)stream, x, (__nv_bfloat16*)x_bf16, mask, cols));
   return MMNAS_OK;
 }
 

@@ -440,6 +440,62 @@ class FFNBlockFn(Function):
 
 
 # ----------------------------------------------------------------------------------------------------------
+# stem: y_in = imgfeat_linear(frcn_feat), y_mask = make_mask(frcn_feat)   (full_vqa.py:91,101,113-114)
+# ----------------------------------------------------------------------------------------------------------
+class StemImageFn(Function):
+    """One pass over the [B, N, 2048] region features produces their bf16 copy and the padding mask; the projection
+    and its weight gradient run on the tcgen05 GEMM (bf16 arm) or the FFMA GEMM (fp32 arm)."""
+
+    @staticmethod
+    def forward(ctx, feat, W, b, precision):
+        require_cuda(feat, W)
+        ctx.set_materialize_grads(False)
+        dev = feat.device
+        feat = feat.contiguous()
+        B, N, Fin = feat.shape
+        H = W.shape[0]
+        M = B * N
+        bf = precision == 'bf16'
+        mask = torch.empty((B, N), dtype=torch.uint8, device=dev)
+        y = _empty((B, N, H), torch.float32, dev)
+        feat16 = None
+        if bf:
+            feat16 = _empty((M, Fin), torch.bfloat16, dev)
+            K.cast_rowmask(feat, feat16, mask, M, Fin)
+            w16 = K.cast_bf16(W.detach())
+            K.gemm_bf16(M, H, Fin, feat16, Fin, 0, w16, Fin, 0, y, H, bias=b)
+        else:
+            K.cast_rowmask(feat, None, mask, M, Fin)
+            K.gemm_f32(M, H, Fin, feat, Fin, 1, W, 1, Fin, y, H, bias=b)
+        ctx.bf, ctx.dims = bf, (M, Fin, H)
+        ctx.params = (W, b)
+        ctx.save_for_backward(feat16 if bf else feat)
+        return y, mask.view(B, 1, 1, N).view(torch.bool)      # bool output: non-differentiable by type
+
+    @staticmethod
+    def backward(ctx, dy, _dmask=None):
+        if dy is None:
+            return None, None, None, None
+        M, Fin, H = ctx.dims
+        W, b = ctx.params
+        x, = ctx.saved_tensors
+        dev = dy.device
+        dy = dy.contiguous().view(M, H)
+        s_W, s_b = _Sink([W], dev), _Sink([b], dev)
+        s_b.prepare(False)
+        K.colsum(dy, M, H, H, s_b.buf, accumulate=s_b.direct)
+        if ctx.bf:
+            dy16 = K.cast_bf16(dy)
+            sk = _split_k(H, Fin, M)
+            s_W.prepare(zero=sk > 1)
+            K.gemm_bf16(H, Fin, M, dy16, H, 1, x, Fin, 1, s_W.buf, Fin, split_k=sk, accumulate=s_W.direct and sk == 1)
+        else:
+            s_W.prepare(False)
+            K.gemm_f32(H, Fin, M, dy, 1, H, x, Fin, 1, s_W.buf, Fin, accumulate=s_W.direct)
+        return None, s_W.grads()[0], s_b.grads()[0], None
+
+
+# ----------------------------------------------------------------------------------------------------------
 # stand-alone LayerNorm (modules.py:44-56) — same kernel with no residual / dropout
 # ----------------------------------------------------------------------------------------------------------
 class LayerNormFn(Function):

@@ -110,6 +110,10 @@ def colsum(x, rows, cols, ld, out, accumulate=False):
     call('mmnas_colsum', _code(x), ptr(x), rows, cols, ld, ptr(out), int(accumulate), stream())
 
 
+def cast_rowmask(x, x16, mask, rows, cols):
+    call('mmnas_cast_rowmask', ptr(x), ptr(x16), ptr(mask), rows, cols, stream())
+
+
 def sumsq(flat, out):
     call('mmnas_sumsq_f32', ptr(flat), flat.numel(), ptr(out), stream())
 

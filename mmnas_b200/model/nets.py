@@ -15,6 +15,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import runtime
+from ..functional import StemImageFn
 from .mixed import MixedOp
 from .modules import AttFlat, LayerNorm, RelGeometry
 from ..utils.ops_adapter import OpsAdapter
@@ -122,11 +124,14 @@ class _NetBase(nn.Module):
     def forward(self, input):
         frcn_feat, bbox_feat, y_rel, ques_ix, x_rel = input
         x_mask = make_mask(ques_ix.unsqueeze(2))
-        y_mask = make_mask(frcn_feat)
         x_in, _ = self.lstm(self.embedding(ques_ix))
-        if self.BBOX_FEATURE:
+        if self.BBOX_FEATURE:       # not used by any shipped config (BBOX_FEATURE = False, train_vqa.py:136): torch path
+            y_mask = make_mask(frcn_feat)
             frcn_feat = torch.cat((frcn_feat, self.bboxfeat_linear(bbox_feat)), dim=-1)
-        y_in = self.imgfeat_linear(frcn_feat)
+            y_in = self.imgfeat_linear(frcn_feat)
+        else:                       # mask + bf16 cast in one pass over the features, projection on our GEMM
+            y_in, y_mask = StemImageFn.apply(frcn_feat, self.imgfeat_linear.weight, self.imgfeat_linear.bias,
+                                             runtime.get_precision())
         # x_rel is never consumed (no relation op is an encoder candidate); the reference still embeds it in
         # Net_Search (hygr_vqa.py:130) — the parameters exist here for checkpoint parity, the dead matmul does not run.
         if self.rel_mode == 'geometry':
