@@ -1,0 +1,96 @@
+"""Data-parallel gradient parity on real GPUs (SURVEY §4 'distributed', §8e): two ranks, each with its own half of a
+batch, must end the backward with the same averaged gradients as one process that sees the concatenated batch and
+divides its sum-reduced loss by the world size (DDP semantics of train_vqa.py:236-237).  Needs >= 2 GPUs: the
+single-GPU round-end run skips it; `gpurun --gpus 2 -- python -m pytest tests/test_gpu_dp.py -m gpu` runs it."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _setup(batch):
+    from mmnas_b200 import genotypes
+    from mmnas_b200.data.synthetic import Cfg, SynthSpec, make_batch, init_dict
+    spec = SynthSpec(batch=batch, vocab=500, n_ans=50)
+    cfg = Cfg(genotype=genotypes.shipped('mmnas_vqa'), DROPOUT_R=0.0)
+    inputs, target = make_batch(spec, seed=11)
+    return spec, cfg, init_dict(spec), inputs, target
+
+
+def _worker(rank, world, port, q):
+    import mmnas_b200
+    from mmnas_b200 import runtime
+    from mmnas_b200.engine import FlatGrads, BucketReducer
+    from mmnas_b200.model.nets import Net_Full
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        mmnas_b200.set_precision('fp32')
+        torch.manual_seed(3)
+        spec, cfg, init, inputs, target = _setup(4 * world)
+        net = Net_Full(cfg, init).to(dev).train()
+        sl = slice(4 * rank, 4 * rank + 4)
+        din, dt = tuple(t[sl].to(dev) for t in inputs), target[sl].to(dev)
+        fg = FlatGrads(net.parameters())
+        red = BucketReducer(fg, bucket_mb=8.0)
+        assert red.enabled and len(red.buckets) > 3
+        fg.zero()
+        red.reset()
+        runtime.direct_grads, runtime.grad_listener = True, red.notify
+        try:
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(net(din), dt, reduction='sum')
+            loss.backward()
+        finally:
+            runtime.direct_grads, runtime.grad_listener = False, None
+        red.finish()
+        torch.cuda.synchronize()
+        q.put((rank, fg.flat.cpu()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+@pytest.mark.timeout(300)
+def test_two_rank_gradients_equal_single_process_on_concatenated_batch():
+    import mmnas_b200
+    from mmnas_b200.engine import FlatGrads
+    from mmnas_b200.model.nets import Net_Full
+    world, port = 2, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    mmnas_b200.set_precision('fp32')
+    torch.manual_seed(3)
+    spec, cfg, init, inputs, target = _setup(4 * world)
+    net = Net_Full(cfg, init).to('cuda:0').train()
+    fg = FlatGrads(net.parameters())
+    fg.zero()
+    pred = net(tuple(t.to('cuda:0') for t in inputs))
+    (torch.nn.functional.binary_cross_entropy_with_logits(pred, target.to('cuda:0'), reduction='sum') / world).backward()
+    ref = fg.flat.cpu()
+    mmnas_b200.set_precision('bf16')
+    assert torch.equal(got[0], got[1])                                   # every rank holds the same averaged gradients
+    scale = ref.abs().max().item()
+    assert (got[0] - ref).abs().max().item() < 2e-5 * scale
