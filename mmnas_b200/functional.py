@@ -54,6 +54,8 @@ def _grad_target(params):
     temporaries.  Otherwise None."""
     if not runtime.direct_grads:
         return None
+    if any(getattr(p, '_mmnas_shared', False) for p in params):
+        return None     # used by several blocks per step: autograd must sum the contributions and fire its hook ONCE
     g0 = params[0].grad
     if g0 is None:
         return None

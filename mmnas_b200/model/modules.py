@@ -31,6 +31,10 @@ class RelGeometry:
         self.g4 = g4
         self.weight = linear.weight
         self.bias = linear.bias
+        # every RSA block of the net contributes to these two gradients: keep them on autograd's accumulation path so
+        # the data-parallel reducer sees ONE completion per step (see functional._grad_target)
+        self.weight._mmnas_shared = True
+        self.bias._mmnas_shared = True
 
     def dense(self):
         return F.relu(F.linear(self.g4, self.weight, self.bias))
