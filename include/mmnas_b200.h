@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MMNAS_B200_ABI_VERSION 4
+#define MMNAS_B200_ABI_VERSION 5
 
 typedef void* mmnas_stream;
 
@@ -106,8 +106,11 @@ int mmnas_colsum(int dtype, const void* x, int rows, int cols, long ld, float* o
 int mmnas_cast_rowmask(const float* x, void* x_bf16, unsigned char* mask, int rows, int cols, mmnas_stream stream);
 
 /* ---- optimizer tail: clip_grad_norm_ (train_vqa.py:310) + Adam (train_vqa.py:311 via optimizer.py:14-20) ------
- * out[0] = sum(x^2) over a flat fp32 buffer (n % 4 == 0). */
-int mmnas_sumsq_f32(const float* x, long n, float* out, mmnas_stream stream);
+ * out[0] = sum(x^2) over a flat fp32 buffer (n % 4 == 0).  Bit-reproducible (fixed summation order, no float
+ * atomics), so data-parallel replicas holding the same gradients clip by the same coefficient.  `scratch` =
+ * MMNAS_SUMSQ_SCRATCH floats of device memory owned by the caller, not shared between concurrent calls. */
+#define MMNAS_SUMSQ_SCRATCH 1280
+int mmnas_sumsq_f32(const float* x, long n, float* out, float* scratch, mmnas_stream stream);
 /* One launch updates every parameter: `table` = DEVICE array of n_chunks rows of 5 int64 {param*, grad*, exp_avg*,
  * exp_avg_sq*, count} (count <= 4096).  Gradients are scaled by min(1, max_norm / (sqrt(*sumsq) + 1e-6))
  * (max_norm <= 0: no clipping); lr is read from device memory, the step count t from step_state[1] (advance it with

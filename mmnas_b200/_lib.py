@@ -10,7 +10,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libmmnas_b200.so')
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 c_p, c_i, c_l, c_f, c_u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float, ctypes.c_ulonglong
 
@@ -34,7 +34,7 @@ SIGNATURES = {
     'mmnas_cast_multi': [c_p, c_i, c_p],
     'mmnas_colsum': [c_i, c_p, c_i, c_i, c_l, c_p, c_i, c_p],
     'mmnas_cast_rowmask': [c_p, c_p, c_p, c_i, c_i, c_p],
-    'mmnas_sumsq_f32': [c_p, c_l, c_p, c_p],
+    'mmnas_sumsq_f32': [c_p, c_l, c_p, c_p, c_p],
     'mmnas_clip_adam': [c_p, c_i, c_p, c_p, c_p, c_f, c_f, c_f, c_f, c_p],
     'mmnas_rng_advance': [c_p, c_p],
 }

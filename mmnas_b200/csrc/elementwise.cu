@@ -186,8 +186,13 @@ __global__ void __launch_bounds__(EW_THREADS) cast_rowmask_kernel(const float* _
 }
 
 // ---- optimizer tail: clip_grad_norm_ + Adam in two passes over flat / tabled buffers ----------
-__global__ void __launch_bounds__(EW_THREADS) sumsq_kernel(const float* __restrict__ x, long n, float* __restrict__ out) {
+// Deterministic: every block stores its partial, the last block to finish adds them in block order.  (An atomicAdd
+// into one float would make the clip coefficient depend on block scheduling, and data-parallel replicas that apply
+// the same averaged gradient would drift apart bit by bit.)  scratch[0] = arrival counter, scratch[1..] = partials.
+__global__ void __launch_bounds__(EW_THREADS) sumsq_kernel(const float* __restrict__ x, long n, float* __restrict__ out,
+                                                           float* __restrict__ scratch) {
   __shared__ float red[EW_THREADS / 32];
+  __shared__ bool last;
   pdl_wait(); pdl_launch();
   float s = 0.f;
   const long nvec = n >> 2;
@@ -198,10 +203,28 @@ __global__ void __launch_bounds__(EW_THREADS) sumsq_kernel(const float* __restri
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
+  unsigned* counter = reinterpret_cast<unsigned*>(scratch);
+  float* partial = scratch + 1;
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int w = 0; w < EW_THREADS / 32; ++w) t += red[w];
-    atomicAdd(out, t);
+    partial[blockIdx.x] = t;
+    __threadfence();
+    last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float t = 0.f;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += EW_THREADS) t += __ldcg(partial + b);   // fixed assignment
+  t = warp_sum(t);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < EW_THREADS / 32; ++w) tot += red[w];
+    *out = tot;
+    *counter = 0u;
   }
 }
 
@@ -328,12 +351,14 @@ extern "C" int mmnas_cast_rowmask(const float* x, void* x_bf16, unsigned char* m
   return MMNAS_OK;
 }
 
-extern "C" int mmnas_sumsq_f32(const float* x, long n, float* out, mmnas_stream stream) {
-  MMNAS_CHECK_ARG(x && out && n >= 0 && (n % 4) == 0 && ((uintptr_t)x % 16) == 0, "sumsq: bad argument (n % 4, 16-byte alignment)");
+extern "C" int mmnas_sumsq_f32(const float* x, long n, float* out, float* scratch, mmnas_stream stream) {
+  MMNAS_CHECK_ARG(x && out && scratch && n >= 0 && (n % 4) == 0 && ((uintptr_t)x % 16) == 0,
+                  "sumsq: bad argument (null buffer, n % 4, 16-byte alignment)");
+  static_assert(148 * 8 + 1 <= MMNAS_SUMSQ_SCRATCH, "scratch too small for the grid cap");
   cudaStream_t s = (cudaStream_t)stream;
-  MMNAS_CUDA(cudaMemsetAsync(out, 0, sizeof(float), s));
-  if (n == 0) return MMNAS_OK;
-  MMNAS_CUDA(mmnas_launch(sumsq_kernel, dim3(ew_grid(n >> 2)), dim3(EW_THREADS), 0, s, x, n, out));
+  if (n == 0) { MMNAS_CUDA(cudaMemsetAsync(out, 0, sizeof(float), s)); return MMNAS_OK; }
+  MMNAS_CUDA(cudaMemsetAsync(scratch, 0, sizeof(unsigned), s));
+  MMNAS_CUDA(mmnas_launch(sumsq_kernel, dim3(ew_grid(n >> 2)), dim3(EW_THREADS), 0, s, x, n, out, scratch));
   return MMNAS_OK;
 }
 

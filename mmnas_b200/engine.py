@@ -76,6 +76,7 @@ class BucketReducer:
             for i in ids:
                 self.bucket_of[i] = b
         self._pending = [0] * len(self.buckets)
+        self._fired = [False] * len(self.fg.params)
         self._launched = [False] * len(self.buckets)
         self._works = []
         self._avg = None
@@ -89,8 +90,9 @@ class BucketReducer:
 
     def _make_hook(self, i):
         def hook(param):
-            if not self._armed:
-                return
+            if not self._armed or self._fired[i]:
+                return                      # (autograd also fires the hook for a gradient returned as None,
+            self._fired[i] = True           #  after notify() already counted the directly written one)
             b = self.bucket_of[i]
             self._pending[b] -= 1
             if self._pending[b] == 0:
@@ -109,6 +111,7 @@ class BucketReducer:
             self._pending[b] = len(ids)
             self._launched[b] = False
         self._works = []
+        self._fired = [False] * len(self.fg.params)
         self._armed = True
 
     def _launch(self, b):
@@ -249,6 +252,7 @@ class FusedClipAdam:
         self.exp_avg = torch.zeros(self.hi - self.lo, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(self.hi - self.lo, dtype=torch.float32, device=dev)
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.scratch = torch.zeros(kernels.SUMSQ_SCRATCH, dtype=torch.float32, device=dev)
         self.lr = torch.zeros(1, dtype=torch.float32, device=dev)
         self.state = torch.zeros(2, dtype=torch.int64, device=dev)        # [unused, step count]
         self.betas, self.eps, self.clip = betas, eps, (clip if clip else 0.0)
@@ -268,7 +272,7 @@ class FusedClipAdam:
         k = self.kernels
         k.rng_advance(self.state)
         if self.clip > 0:
-            k.sumsq(self.grad_range, self.sumsq)
+            k.sumsq(self.grad_range, self.sumsq, self.scratch)
         k.clip_adam(self.table, self.n_chunks, self.sumsq, self.lr, self.state, self.betas[0], self.betas[1], self.eps,
                     float(self.clip))
 

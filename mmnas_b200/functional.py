@@ -120,6 +120,8 @@ class _Sink:
         return self
 
     def grads(self):
+        """Call after fork.join(): in direct mode this tells the data-parallel reducer the gradients are complete,
+        and the reducer may enqueue the bucket's all-reduce behind the CURRENT stream right away."""
         if self.direct:
             runtime.notify_grads(self.params)
             return (None,) * len(self.params)
@@ -308,7 +310,6 @@ class AttBlockFn(Function):
         if self_att:
             s_vkq = _Sink([Wv, Wk, Wq], dev)
             wgrad(s_vkq, 3 * I, H, Mq, dqkv, 3 * I, x16, H, dqkv, x)
-            g_Wv, g_Wk, g_Wq = s_vkq.grads()
             if bf:
                 K.gemm_bf16(Mq, H, 3 * I, dqkv, 3 * I, 0, cfg.w16['vkq'], H, 1, dz, H, accumulate=not fresh_dz)
             else:
@@ -321,8 +322,6 @@ class AttBlockFn(Function):
             s_q, s_vk = _Sink([Wq], dev), _Sink([Wv, Wk], dev)
             wgrad(s_q, I, H, Mq, dqkv, I, x16, H, dqkv, x)
             wgrad(s_vk, 2 * I, H, Mk, dkvb, 2 * I, kv16, H, dkvb, kvt)
-            g_Wq, = s_q.grads()
-            g_Wv, g_Wk = s_vk.grads()
             if bf:
                 K.gemm_bf16(Mq, H, I, dqkv, I, 0, cfg.w16['q'], H, 1, dz, H, accumulate=not fresh_dz)
                 K.gemm_bf16(Mk, H, 2 * I, dkvb, 2 * I, 0, cfg.w16['vk'], H, 1, dkv_in, H)
@@ -332,6 +331,11 @@ class AttBlockFn(Function):
                 K.gemm_f32(Mk, H, I, dk, 2 * I, 1, Wk, H, 1, dkv_in, H, accumulate=True)
             dkv_in = dkv_in.view(B, Nk, H)
         fork.join()
+        if self_att:
+            g_Wv, g_Wk, g_Wq = s_vkq.grads()
+        else:
+            g_Wq, = s_q.grads()
+            g_Wv, g_Wk = s_vk.grads()
         g_a2 = s_a2.grads()[0] if norm else None
         g_b2 = s_b2.grads()[0] if norm else None
         return (dz.view(B, Nq, H), dkv_in, g_Wq, g_Wk, g_Wv, s_m.grads()[0], g_a2, g_b2, drel, None, g_Wy, g_by, g_Wr,

@@ -114,8 +114,12 @@ def cast_rowmask(x, x16, mask, rows, cols):
     call('mmnas_cast_rowmask', ptr(x), ptr(x16), ptr(mask), rows, cols, stream())
 
 
-def sumsq(flat, out):
-    call('mmnas_sumsq_f32', ptr(flat), flat.numel(), ptr(out), stream())
+SUMSQ_SCRATCH = 1280      # MMNAS_SUMSQ_SCRATCH floats
+
+
+def sumsq(flat, out, scratch):
+    assert scratch.numel() >= SUMSQ_SCRATCH and scratch.dtype == torch.float32
+    call('mmnas_sumsq_f32', ptr(flat), flat.numel(), ptr(out), ptr(scratch), stream())
 
 
 def clip_adam(table, n_chunks, sumsq_buf, lr, step_state, beta1, beta2, eps, max_norm):

@@ -30,7 +30,37 @@ def _forward(m, x):
     return m[4](m[3](m[2](m[1](m[0](x)))))      # m[5] never runs: its grads must still arrive as zeros
 
 
-def _worker(rank, world, port, q):
+class _DirectLinear(torch.autograd.Function):
+    """What the block backwards do in direct-gradient mode: accumulate into p.grad in place, tell the reducer through
+    runtime.notify_grads and hand autograd None (autograd STILL fires the post-accumulate hook for that None)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.set_materialize_grads(False)
+        ctx.params = (w, b)
+        ctx.save_for_backward(x)
+        return x @ w.detach().t() + b.detach()
+
+    @staticmethod
+    def backward(ctx, g):
+        from mmnas_b200 import runtime
+        x, = ctx.saved_tensors
+        w, b = ctx.params
+        w.grad += g.t() @ x
+        b.grad += g.sum(0)
+        runtime.notify_grads([w, b])
+        return g @ w.detach(), None, None
+
+
+def _forward_direct(m, x):
+    for i in (0, 2, 4):
+        x = _DirectLinear.apply(x, m[i].weight, m[i].bias)
+        if i < 4:
+            x = torch.relu(x)
+    return x
+
+
+def _worker(rank, world, port, q, direct=False):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
@@ -46,8 +76,18 @@ def _worker(rank, world, port, q):
         for _ in range(2):                                  # second pass checks re-arming
             fg.zero()
             red.reset()
-            loss = ((_forward(m, xs) - ys) ** 2).sum()
-            loss.backward()
+            if direct:
+                from mmnas_b200 import runtime
+                runtime.grad_listener = red.notify
+                xs = xs.clone().requires_grad_(True)
+                loss = ((_forward_direct(m, xs) - ys) ** 2).sum()
+                loss.backward()
+                runtime.grad_listener = None
+            else:
+                loss = ((_forward(m, xs) - ys) ** 2).sum()
+                loss.backward()
+            early = [b for b, (_, _, ids) in enumerate(red.buckets) if red._launched[b] and red._pending[b] != 0]
+            assert not early, f'buckets {early} were reduced before all their parameters reported'
             red.finish()
         q.put((rank, fg.flat.clone()))
     finally:
@@ -55,11 +95,12 @@ def _worker(rank, world, port, q):
 
 
 @pytest.mark.timeout(120)
-def test_bucket_reducer_matches_single_process_gradients():
+@pytest.mark.parametrize('direct', [False, True], ids=['autograd_grads', 'direct_grads'])
+def test_bucket_reducer_matches_single_process_gradients(direct):
     world, port = 2, _free_port()
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, direct)) for r in range(world)]
     for p in procs:
         p.start()
     got = dict(q.get(timeout=100) for _ in range(world))

@@ -349,3 +349,24 @@ def test_fused_clip_adam_matches_torch():
     for p, q in zip(ps_a, ps_b):
         assert normwise(p, q) < 2e-6
     assert abs(fused._rate - 0.75e-2) < 1e-12 and fused.rate(1) == 2.5e-3      # step 5 of 2-step 'epochs': 3/4 warm-up
+
+
+def test_sumsq_is_bit_reproducible_and_exact_enough():
+    """The gradient-norm reduction feeds the clip coefficient of every replica: it must not depend on block
+    scheduling (no float atomics), and it must match a float64 sum."""
+    k = K()
+    torch.manual_seed(1)
+    x = torch.randn(58_000_004 // 4 * 4, device=DEV) * 0.01          # about the size of the MMnas-VQA gradient buffer
+    out = torch.zeros(1, device=DEV)
+    scratch = torch.zeros(k.SUMSQ_SCRATCH, device=DEV)
+    vals = set()
+    for _ in range(20):
+        k.sumsq(x, out, scratch)
+        vals.add(float(out))
+    assert len(vals) == 1
+    ref = float((x.double() ** 2).sum())
+    assert abs(vals.pop() - ref) < 1e-5 * ref
+    k.sumsq(x[:0], out, scratch)
+    assert float(out) == 0.0
+    k.sumsq(x[:8], out, scratch)                                      # one block
+    assert abs(float(out) - float((x[:8].double() ** 2).sum())) < 1e-6
