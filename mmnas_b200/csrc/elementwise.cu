@@ -352,7 +352,7 @@ extern "C" int mmnas_cast_rowmask(const float* x, void* x_bf16, unsigned char* m
 }
 
 extern "C" int mmnas_sumsq_f32(const float* x, long n, float* out, float* scratch, mmnas_stream stream) {
-  MMNAS_CHECK_ARG(x && out && scratch && n >= 0 && (n % 4) == 0 && ((uintptr_t)x % 16) == 0,
+  MMNAS_CHECK_ARG(out && scratch && n >= 0 && (n % 4) == 0 && (n == 0 || (x && ((uintptr_t)x % 16) == 0)),
                   "sumsq: bad argument (null buffer, n % 4, 16-byte alignment)");
   static_assert(148 * 8 + 1 <= MMNAS_SUMSQ_SCRATCH, "scratch too small for the grid cap");
   cudaStream_t s = (cudaStream_t)stream;
