@@ -126,7 +126,9 @@ __global__ void __launch_bounds__(128, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                    const __grid_constant__ CUtensorMap tv, AttnTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by POINTER arithmetic on the shared array: an integer round trip loses the address space
+  // and every staging access becomes a generic ST.E / LD.E instead of STS / LDS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sQ = smem_u32(smem), sK = sQ + TILE_BYTES, sV = sK + TILE_BYTES, sP = sV + TILE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * TILE_BYTES + PTILE_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);

@@ -11,10 +11,9 @@
 //   share the A tile in L2.  Warp 0 = TMA producer (STAGES-deep smem ring), warp 1 = MMA issuer (one elected lane)
 //   + TMEM allocator, warps 2..9 = epilogue (two warps per TMEM lane quarter, alternating column chunks).  TMEM holds TWO accumulator buffers, so the epilogue of unit i
 //   overlaps the main loop of unit i+1 (v1 paid prologue + fill + epilogue serially per tile and ran at 10 %).
-//   Epilogue: tcgen05.ld (each warp owns the 32 TMEM lanes of its warp%4 quarter) -> padded smem staging ->
-//   re-read row-contiguous, so every global access is a full 64/128-byte row segment; all fused epilogue math
-//   (+bias, ReLU, dropout with one hash per 4 elements, ReLU-mask of a saved activation, fp32 accumulate,
-//   bf16/fp32 store, split-K red.add.v4) happens in that coalesced layout.
+//   Epilogue: tcgen05.ld (each warp owns the 32 TMEM lanes of its warp%4 quarter; a lane holds one row x 32 columns)
+//   -> fused math in registers (+bias, ReLU, dropout with one hash per 4 elements, ReLU-mask of a saved activation)
+//   -> 128B-swizzled smem box -> TMA tile store (bf16 / fp32) or TMA f32 reduce-add (accumulate, split-K).
 //   BN = 256 (single 128x256x16 UMMA, half the operand traffic per FLOP) when it does not cost a wave.
 #include <cstdlib>
 #include "tc_common.cuh"
@@ -26,8 +25,8 @@ constexpr int BM = 128, BK = 64;
 constexpr int A_TILE_BYTES = BM * BK * 2;
 constexpr int NUM_THREADS = 320;                      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int EPI_WARPS = 8;
-constexpr int STG_PITCH = 36;                         // floats per staged row (32 + 4 pad: 16B aligned, conflict free)
-constexpr int STG_BYTES = EPI_WARPS * 32 * STG_PITCH * 4;   // one 32-row staging block per epilogue warp
+constexpr int STG_BOX_BYTES = 32 * 128;               // one TMA-store box: 32 rows x 128 B (64 bf16 / 32 fp32 columns)
+constexpr int STG_BYTES = EPI_WARPS * 2 * STG_BOX_BYTES;    // two boxes per epilogue warp (store i+1 is built while i drains)
 
 template <int BN> struct Cfg {
   static constexpr int STAGES = BN == 128 ? 5 : 3;
@@ -47,59 +46,148 @@ struct TcEpilogue {
   int use_drop; DropCfg drop;
   int split_k;                       // > 1: fp32 red.add into C
   int tiles_m, tiles_n, kb_total, kb_per;
+  int debug;                         // tuning only (MMNAS_GEMM_DEBUG): 2 = no MMA issue, 3 = no epilogue work
 };
 
-__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+// ---- epilogue: TMEM -> registers -> (bias, ReLU, dropout, ReLU-mask) -> 128B-swizzled smem box -> TMA store ----------
+// tcgen05.ld 32x32b gives every lane ONE accumulator row x 32 consecutive columns, which is already the layout all the
+// fused epilogue math wants (the dropout hash covers 4 consecutive columns of a row).  The row is written as 16-byte
+// chunks into a [32 rows][128 B] box with the TMA 128B swizzle (chunk ^= row & 7: conflict-free for STS.128), and one
+// lane hands the box to the TMA unit: plain tile store for bf16 / fp32 outputs, f32 reduce-add for `accumulate`
+// and for split-K.  Row and column clipping at the tensor edge is done by the TMA unit.  The previous epilogue
+// (padded smem transpose + per-element address math and predicates) issued ~545 instructions per 32x32 chunk and
+// made every projection epilogue-bound at 2x the main-loop time; this one issues ~100.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// epilogue math on 4 consecutive columns of one row, then the store — all accesses row-contiguous
-__device__ __forceinline__ void epilogue_store4(const TcEpilogue& ep, float4 v, int row, int col, const float4& b, uint64_t key,
-                                                const float4& old, const uint2& auxpk) {
-  v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-  if (ep.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-  if (ep.use_drop) {      // same stream as drop_mult(): one 64-bit hash per group of 4 elements
-    const uint64_t idx = (uint64_t)row * ep.N + col;
-    const uint64_t r = mmnas_mix64(key ^ ((idx >> 2) * 0x9E3779B97F4A7C15ull));
-    v.x *= ((unsigned)(r) & 0xFFFFu) < ep.drop.thresh ? 0.f : ep.drop.scale;
-    v.y *= ((unsigned)(r >> 16) & 0xFFFFu) < ep.drop.thresh ? 0.f : ep.drop.scale;
-    v.z *= ((unsigned)(r >> 32) & 0xFFFFu) < ep.drop.thresh ? 0.f : ep.drop.scale;
-    v.w *= ((unsigned)(r >> 48) & 0xFFFFu) < ep.drop.thresh ? 0.f : ep.drop.scale;
-  }
-  if (ep.aux) {
-    const uint2 pk = auxpk;
-    const __nv_bfloat162 a01 = *reinterpret_cast<const __nv_bfloat162*>(&pk.x);
-    const __nv_bfloat162 a23 = *reinterpret_cast<const __nv_bfloat162*>(&pk.y);
-    v.x = __low2float(a01) > 0.f ? v.x * ep.aux_scale : 0.f;
-    v.y = __high2float(a01) > 0.f ? v.y * ep.aux_scale : 0.f;
-    v.z = __low2float(a23) > 0.f ? v.z * ep.aux_scale : 0.f;
-    v.w = __high2float(a23) > 0.f ? v.w * ep.aux_scale : 0.f;
-  }
-  if (ep.out_bf16) {
-    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-    uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&lo);
-    pk.y = *reinterpret_cast<uint32_t*>(&hi);
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(ep.C) + (long)row * ep.ldc + col) = pk;
-  } else {
-    float* cp = reinterpret_cast<float*>(ep.C) + (long)row * ep.ldc + col;
-    if (ep.split_k > 1) {
-      red_add_v4(cp, v);
-    } else {
-      v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;    // zeros unless ep.accumulate
-      *reinterpret_cast<float4*>(cp) = v;
+// fused math on this lane's 32 consecutive columns [col0, col0+32) of row `row`
+__device__ __forceinline__ void epilogue_math(const TcEpilogue& ep, float (&v)[32], int row, int col0, bool add_bias, uint64_t key,
+                                              const uint4 (&aux)[4]) {
+  if (add_bias) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + g);     // same address in every lane
+      v[4 * g] += b.x; v[4 * g + 1] += b.y; v[4 * g + 2] += b.z; v[4 * g + 3] += b.w;
     }
+  }
+  if (ep.relu) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (ep.use_drop) {      // same stream as drop_mult(): one 64-bit hash per group of 4 elements
+    const uint64_t idx4 = ((uint64_t)row * ep.N + col0) >> 2;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const uint64_t r = mmnas_mix64(key ^ ((idx4 + g) * 0x9E3779B97F4A7C15ull));
+      v[4 * g] *= ((unsigned)(r) & 0xFFFFu) < ep.drop.thresh ? 0.f : ep.drop.scale;
+      v[4 * g + 1] *= ((unsigned)(r >> 16) & 0xFFFFu) < ep.drop.thresh ? 0.f : ep.drop.scale;
+      v[4 * g + 2] *= ((unsigned)(r >> 32) & 0xFFFFu) < ep.drop.thresh ? 0.f : ep.drop.scale;
+      v[4 * g + 3] *= ((unsigned)(r >> 48) & 0xFFFFu) < ep.drop.thresh ? 0.f : ep.drop.scale;
+    }
+  }
+  if (ep.aux) {           // v = aux > 0 ? v * aux_scale : 0  (backward through ReLU + dropout-scale of the FFN hidden layer)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t w[4] = {aux[q].x, aux[q].y, aux[q].z, aux[q].w};
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const __nv_bfloat162 a2 = *reinterpret_cast<const __nv_bfloat162*>(&w[h]);
+        const int i = 8 * q + 2 * h;
+        v[i] = __low2float(a2) > 0.f ? v[i] * ep.aux_scale : 0.f;
+        v[i + 1] = __high2float(a2) > 0.f ? v[i + 1] * ep.aux_scale : 0.f;
+      }
+    }
+  }
+}
+
+// One accumulator tile of 32 rows (this warp's TMEM lane quarter) x BN columns.  `tmem_acc` = TMEM address of column 0
+// of the accumulator in this warp's lane quarter; the two warps of a quarter (half = 0 / 1) alternate over the store
+// boxes (64 columns for bf16, 32 for fp32).  `stg` = shared address of this warp's two boxes, `sel` = which is next.
+template <int BN>
+__device__ __forceinline__ void epilogue_unit(const TcEpilogue& ep, const CUtensorMap* tmap_c, uint32_t tmem_acc, uint32_t stg,
+                                              uint32_t& sel, int row0, int n0, int half, bool add_bias, uint64_t key, int lane) {
+  const int row = row0 + lane;
+  const bool row_ok = row < ep.M;
+  const bool reduce = ep.accumulate || ep.split_k > 1;
+  const uint32_t swz = (uint32_t)(lane & 7);
+  const int chunks_per_box = ep.out_bf16 ? 2 : 1;
+  const int boxes = BN / 32 / chunks_per_box;
+#pragma unroll 1
+  for (int bx = half; bx < boxes; bx += 2) {
+    const int colb = n0 + bx * chunks_per_box * 32;
+    if (colb >= ep.N) break;                  // warp-uniform
+    const uint32_t box = stg + sel * STG_BOX_BYTES;
+    const uint32_t rowaddr = box + (uint32_t)lane * 128u;
+    if (lane == 0) bulk_wait_read<1>();       // the store issued two boxes ago has finished reading this buffer
+    __syncwarp();
+#pragma unroll 1
+    for (int c = 0; c < chunks_per_box; ++c) {
+      const int col0 = colb + c * 32;
+      if (col0 >= ep.N) break;                // N % 64 == 32: the TMA unit clips the missing half of the box
+      uint4 aux[4] = {};
+      if (ep.aux && row_ok) {
+        const uint4* ap = reinterpret_cast<const uint4*>(ep.aux + (long)row * ep.ld_aux + col0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) aux[q] = __ldg(ap + q);
+      }
+      uint32_t r[32];
+      tmem_ld32(tmem_acc + (uint32_t)((bx * chunks_per_box + c) * 32), r);
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+      epilogue_math(ep, v, row, col0, add_bias, key, aux);
+      if (ep.out_bf16) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {         // 16-byte chunk (4c + q) of the 128-byte row: 8 bf16 columns
+          uint32_t pk[4];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const __nv_bfloat162 t = __floats2bfloat162_rn(v[8 * q + 2 * h], v[8 * q + 2 * h + 1]);
+            pk[h] = *reinterpret_cast<const uint32_t*>(&t);
+          }
+          sts128(rowaddr + ((((uint32_t)(4 * c + q)) ^ swz) << 4), pk[0], pk[1], pk[2], pk[3]);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)           // 16-byte chunk q: 4 fp32 columns
+          sts128(rowaddr + (((uint32_t)q ^ swz) << 4), __float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]),
+                 __float_as_uint(v[4 * q + 2]), __float_as_uint(v[4 * q + 3]));
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA unit
+    __syncwarp();
+    if (lane == 0) {
+      if (reduce) tma_reduce_add_2d(tmap_c, box, colb, row0);
+      else tma_store_2d(tmap_c, box, colb, row0);
+      bulk_commit();
+    }
+    sel ^= 1u;
   }
 }
 
 template <bool A_MN, bool B_MN, int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, TcEpilogue ep) {
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_c, TcEpilogue ep) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  float* staging = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES);
+  // 1024-byte alignment by POINTER arithmetic on the shared array: an integer round trip loses the address space
+  // and every staging access becomes a generic ST.E / LD.E instead of STS / LDS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t staging = smem_u32(smem) + STAGES * C::STAGE_BYTES;      // 1024-byte aligned (swizzle atom)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES + STG_BYTES);
   // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty; then the TMEM base word
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
@@ -116,6 +204,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_c) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -128,6 +217,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  // Let the next kernel of the stream be scheduled now: its CTAs land on SMs this grid leaves idle (28..112 CTAs for
+  // the text-stream projections) or free first, run their own prologue and park in griddepcontrol.wait.
+  if (threadIdx.x == 0) pdl_launch();
 
   // unit -> (split z, m-tile, n-tile), n fastest
   auto decode = [&](int u, int& z, int& m0, int& n0, int& kb0, int& nkb) {
@@ -167,7 +259,6 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       }
     }
-    pdl_launch();                                 // all loads issued: the next kernel may start its prologue
   } else if (warp == 1 && lane == 0) {
     // ===== MMA issuer =====
     constexpr uint32_t idesc = make_idesc(A_MN, B_MN, BM, BN);
@@ -190,75 +281,199 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           // MN-major: 16 k-rows x 128 B = 2048 B; SBO = 8 k-rows x 128 B, LBO = next 64-wide MN chunk.
           const uint64_t adesc = A_MN ? make_smem_desc(sa + kk * 2048, BK * 128, 1024) : make_smem_desc(sa + kk * 32, 16, 1024);
           const uint64_t bdesc = B_MN ? make_smem_desc(sb + kk * 2048, BK * 128, 1024) : make_smem_desc(sb + kk * 32, 16, 1024);
-          umma_bf16(tmem_d, adesc, bdesc, idesc, (i | kk) != 0 ? 1u : 0u);
+          if (ep.debug != 2) umma_bf16(tmem_d, adesc, bdesc, idesc, (i | kk) != 0 ? 1u : 0u);
         }
         umma_commit(empty_bar(s));        // frees the smem stage when these MMAs retire
       }
       umma_commit(tfull_bar(buf));        // accumulator of this unit complete
     }
   } else if (warp >= 2) {
-    // ===== epilogue: TMEM -> registers -> smem staging -> coalesced global =====
+    // ===== epilogue =====
     // Eight warps: warp%4 selects the TMEM lane quarter (hardware rule), the two warps of a quarter alternate
-    // over the 32-column chunks, so the epilogue keeps up with a 128 x BN x 512 main loop.
+    // over the store boxes, so the epilogue keeps up with a 128 x BN x 512 main loop.
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32)
     const int half = (warp - 2) >> 2;             // 0: warps 2..5, 1: warps 6..9
-    pdl_wait();                                   // this warp reads (accumulate / aux / bias) and writes global memory
-    float* stg = staging + (warp - 2) * (32 * STG_PITCH);
+    pdl_wait();                                   // this warp reads (aux / bias) and writes global memory
+    const uint32_t stg = staging + (uint32_t)(warp - 2) * (2 * STG_BOX_BYTES);
     const uint64_t key = ep.use_drop ? drop_key(ep.drop) : 0;
-    const int sub_r = lane >> 3, col4 = (lane & 7) * 4;
-    uint32_t j = 0;
+    uint32_t j = 0, sel = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x, ++j) {
       int z, m0, n0, kb0, nkb;
       decode(u, z, m0, n0, kb0, nkb);
       const uint32_t buf = j & 1;
       mbar_wait(tfull_bar(buf), (j >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const bool add_bias = ep.bias != nullptr && z == 0;
-      const int row_base = m0 + quarter * 32;
-#pragma unroll 1
-      for (int cc = half; cc < BN / 32; cc += 2) {
-        const int col0 = n0 + cc * 32;
-        if (col0 >= ep.N) break;                  // warp-uniform (N % 32 == 0)
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + cc * 32), r);
-#pragma unroll
-        for (int g = 0; g < 8; ++g)
-          *reinterpret_cast<uint4*>(stg + lane * STG_PITCH + 4 * g) = make_uint4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
-        __syncwarp();
-        // all global reads of the chunk (old C for accumulate, the ReLU-mask activation, bias) are issued before
-        // any dependent math, so their latencies overlap instead of serialising 8 load->add->store chains
-        const int col = col0 + col4;
-        float4 bia = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (add_bias) bia = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
-        float4 old[8];
-        uint2 auxpk[8];
-#pragma unroll
-        for (int itr = 0; itr < 8; ++itr) {
-          const int row = row_base + itr * 4 + sub_r;
-          old[itr] = make_float4(0.f, 0.f, 0.f, 0.f);
-          auxpk[itr] = make_uint2(0u, 0u);
-          if (row < ep.M) {
-            if (ep.accumulate) old[itr] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.C) + (long)row * ep.ldc + col);
-            if (ep.aux) auxpk[itr] = __ldg(reinterpret_cast<const uint2*>(ep.aux + (long)row * ep.ld_aux + col));
-          }
-        }
-#pragma unroll
-        for (int itr = 0; itr < 8; ++itr) {
-          const int rr = itr * 4 + sub_r;
-          const int row = row_base + rr;
-          const float4 v = *reinterpret_cast<const float4*>(stg + rr * STG_PITCH + col4);
-          if (row < ep.M) epilogue_store4(ep, v, row, col, bia, key, old[itr], auxpk[itr]);
-        }
-        __syncwarp();
-      }
+      if (ep.debug != 3)
+        epilogue_unit<BN>(ep, &tmap_c, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN), stg, sel,
+                          m0 + quarter * 32, n0, half, ep.bias != nullptr && z == 0, key, lane);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       if (lane == 0) mbar_arrive(tempty_bar(buf));
     }
+    if (lane == 0) bulk_wait<0>();                // every store / reduce of this warp has been performed
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): a cluster of two CTAs on one TPC owns a 256 x 256 output tile.  Each CTA
+// stages its own 128 rows of A and its own 128 of the 256 B rows; ONE 256x256x16 MMA issued by the leader reads
+// both CTAs' shared memory and writes 128 accumulator rows into each CTA's TMEM.  Per 128x256 of output a CTA pulls
+// 32 KB per k-block through L2 instead of 48 KB (1-CTA, BN=256) or 64 KB (BN=128) — the projections of this model
+// (K = 512) are bound by exactly that L2->SM traffic, not by the tensor pipe (GEMM section).
+//   full[s]   : leader's barrier; the leader arms it with the bytes of BOTH CTAs, both CTAs' TMA complete on it
+//   empty[s]  : one per CTA, released by the leader's multicast commit once the MMAs reading the stage retired
+//   tfull[b]  : one per CTA, multicast commit after the last MMA of a unit
+//   tempty[b] : leader's barrier, 2 x EPI_WARPS arrivals (the peer's epilogue warps arrive remotely)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int PAIR_BN = 256;                          // N of the pair tile; each CTA stages PAIR_BN / 2 rows of B
+constexpr int PAIR_STAGES = 5;
+constexpr int PAIR_STAGE_BYTES = A_TILE_BYTES + (PAIR_BN / 2) * BK * 2;
+constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + STG_BYTES + 1024 + 256;
+constexpr uint32_t PAIR_TMEM_COLS = 2 * PAIR_BN;
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const __grid_constant__ CUtensorMap tmap_c, TcEpilogue ep) {
+  constexpr int STAGES = PAIR_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // both CTAs must use identical shared-memory offsets: the MMA applies the leader's descriptors in the peer too
+  // 1024-byte alignment by POINTER arithmetic on the shared array: an integer round trip loses the address space
+  // and every staging access becomes a generic ST.E / LD.E instead of STS / LDS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t staging = smem_u32(smem) + STAGES * PAIR_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * PAIR_STAGE_BYTES + STG_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int units = ep.tiles_m * ep.tiles_n * ep.split_k;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_c) : "memory");
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 2 * EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {      // one warp of EACH CTA: the pair allocation is collective
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(PAIR_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();                               // the peer's barriers exist before anything signals them
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) pdl_launch();
+
+  auto decode = [&](int u, int& z, int& m0, int& n0, int& kb0, int& nkb) {
+    const int tn = u % ep.tiles_n;
+    const int rest = u / ep.tiles_n;
+    const int tm = rest % ep.tiles_m;
+    z = rest / ep.tiles_m;
+    m0 = tm * (2 * BM) + (int)rank * BM;            // this CTA's 128 rows of the 256-row tile
+    n0 = tn * PAIR_BN;
+    kb0 = z * ep.kb_per;
+    nkb = min(ep.kb_total, kb0 + ep.kb_per) - kb0;
+  };
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer (both CTAs) =====
+    pdl_wait();
+    uint32_t it = 0;
+    for (int u = cluster_id; u < units; u += n_clusters) {
+      int z, m0, n0, kb0, nkb;
+      decode(u, z, m0, n0, kb0, nkb);
+      const int nh = n0 + (int)rank * (PAIR_BN / 2);           // this CTA's half of the B rows
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(empty_bar(s), ((it / STAGES) & 1) ^ 1);
+        if (leader) mbar_expect_tx(full_bar(s), 2 * PAIR_STAGE_BYTES);
+        const uint32_t fb = mapa_shared(full_bar(s), 0);
+        const uint32_t sa = smem_base + s * PAIR_STAGE_BYTES, sb = sa + A_TILE_BYTES;
+        const int k0 = (kb0 + i) * BK;
+        if (!A_MN) {
+          tma_load_2d_pair(sa, &tmap_a, fb, k0, m0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < BM / 64; ++c) tma_load_2d_pair(sa + c * (BK * 128), &tmap_a, fb, m0 + 64 * c, k0);
+        }
+        if (!B_MN) {
+          tma_load_2d_pair(sb, &tmap_b, fb, k0, nh);
+        } else {
+#pragma unroll
+          for (int c = 0; c < PAIR_BN / 128; ++c) tma_load_2d_pair(sb + c * (BK * 128), &tmap_b, fb, nh + 64 * c, k0);
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ===== MMA issuer (leader CTA only) =====
+    constexpr uint32_t idesc = make_idesc(A_MN, B_MN, 2 * BM, PAIR_BN);
+    uint32_t it = 0, j = 0;
+    for (int u = cluster_id; u < units; u += n_clusters, ++j) {
+      int z, m0, n0, kb0, nkb;
+      decode(u, z, m0, n0, kb0, nkb);
+      const uint32_t buf = j & 1;
+      mbar_wait_cluster(tempty_bar(buf), ((j >> 1) & 1) ^ 1);  // both CTAs' epilogues drained this accumulator
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tmem_d = tmem_base + buf * PAIR_BN;
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(full_bar(s), (it / STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_base + s * PAIR_STAGE_BYTES, sb = sa + A_TILE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) {
+          const uint64_t adesc = A_MN ? make_smem_desc(sa + kk * 2048, BK * 128, 1024) : make_smem_desc(sa + kk * 32, 16, 1024);
+          const uint64_t bdesc = B_MN ? make_smem_desc(sb + kk * 2048, BK * 128, 1024) : make_smem_desc(sb + kk * 32, 16, 1024);
+          if (ep.debug != 2) umma_bf16_pair(tmem_d, adesc, bdesc, idesc, (i | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit_pair(empty_bar(s), 3);
+      }
+      umma_commit_pair(tfull_bar(buf), 3);
+    }
+  } else if (warp >= 2) {
+    // ===== epilogue (both CTAs, each its own 128 accumulator rows) =====
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    pdl_wait();
+    const uint32_t stg = staging + (uint32_t)(warp - 2) * (2 * STG_BOX_BYTES);
+    const uint64_t key = ep.use_drop ? drop_key(ep.drop) : 0;
+    const uint32_t te0 = mapa_shared(tempty_bar(0), 0), te1 = mapa_shared(tempty_bar(1), 0);
+    uint32_t j = 0, sel = 0;
+    for (int u = cluster_id; u < units; u += n_clusters, ++j) {
+      int z, m0, n0, kb0, nkb;
+      decode(u, z, m0, n0, kb0, nkb);
+      const uint32_t buf = j & 1;
+      mbar_wait(tfull_bar(buf), (j >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (ep.debug != 3)
+        epilogue_unit<PAIR_BN>(ep, &tmap_c, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * PAIR_BN), stg, sel,
+                               m0 + quarter * 32, n0, half, ep.bias != nullptr && z == 0, key, lane);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      if (lane == 0) mbar_arrive_cluster(buf ? te1 : te0);
+    }
+    if (lane == 0) bulk_wait<0>();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();                               // no CTA leaves (or frees TMEM) while its peer still works
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(PAIR_TMEM_COLS) : "memory");
   }
 }
 
@@ -273,7 +488,7 @@ int num_sms() {
 }
 
 template <bool A_MN, bool B_MN, int BN>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcEpilogue& ep, cudaStream_t s) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcEpilogue& ep, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
     MMNAS_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<A_MN, B_MN, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
@@ -281,16 +496,36 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcEpilogue& ep, c
   }
   const int units = ep.tiles_m * ep.tiles_n * ep.split_k;
   const int grid = units < num_sms() ? units : num_sms();
-  MMNAS_CUDA(mmnas_launch(gemm_bf16_tc_kernel<A_MN, B_MN, BN>, dim3(grid), dim3(NUM_THREADS), Cfg<BN>::SMEM_BYTES, s, ta, tb, ep));
+  MMNAS_CUDA(mmnas_launch(gemm_bf16_tc_kernel<A_MN, B_MN, BN>, dim3(grid), dim3(NUM_THREADS), Cfg<BN>::SMEM_BYTES, s, ta, tb, tc, ep));
   return MMNAS_OK;
 }
 
 template <int BN>
-int dispatch(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TcEpilogue& ep, cudaStream_t s) {
-  if (!a_mn && !b_mn) return launch<false, false, BN>(ta, tb, ep, s);
-  if (!a_mn && b_mn) return launch<false, true, BN>(ta, tb, ep, s);
-  if (a_mn && !b_mn) return launch<true, false, BN>(ta, tb, ep, s);
-  return launch<true, true, BN>(ta, tb, ep, s);
+int dispatch(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcEpilogue& ep, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch<false, false, BN>(ta, tb, tc, ep, s);
+  if (!a_mn && b_mn) return launch<false, true, BN>(ta, tb, tc, ep, s);
+  if (a_mn && !b_mn) return launch<true, false, BN>(ta, tb, tc, ep, s);
+  return launch<true, true, BN>(ta, tb, tc, ep, s);
+}
+
+template <bool A_MN, bool B_MN>
+int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcEpilogue& ep, cudaStream_t s) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    MMNAS_CUDA(cudaFuncSetAttribute(gemm_bf16_pair_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES));
+    attr_done = true;
+  }
+  const int units = ep.tiles_m * ep.tiles_n * ep.split_k;
+  const int clusters = units < num_sms() / 2 ? units : num_sms() / 2;
+  MMNAS_CUDA(mmnas_launch(gemm_bf16_pair_kernel<A_MN, B_MN>, dim3(2 * clusters), dim3(NUM_THREADS), PAIR_SMEM_BYTES, s, ta, tb, tc, ep));
+  return MMNAS_OK;
+}
+
+int dispatch_pair(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcEpilogue& ep, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch_pair<false, false>(ta, tb, tc, ep, s);
+  if (!a_mn && b_mn) return launch_pair<false, true>(ta, tb, tc, ep, s);
+  if (a_mn && !b_mn) return launch_pair<true, false>(ta, tb, tc, ep, s);
+  return launch_pair<true, true>(ta, tb, tc, ep, s);
 }
 
 }  // namespace
@@ -317,21 +552,39 @@ extern "C" int mmnas_gemm_bf16(int M, int N, int K, const void* A, long lda, int
   MMNAS_CHECK_ARG(!aux || (ld_aux % 8 == 0 && ((uintptr_t)aux % 8) == 0), "gemm_bf16: aux pitch / alignment");
   int kb_per = ceil_div(kb_total, split_k);
   split_k = ceil_div(kb_total, kb_per);                 // no empty splits
-  // BN = 256 halves operand traffic per FLOP; take it unless it costs an extra wave (or multiplies split-K atomics)
+  // Tile configuration from a small cost model fitted on B200 (scripts/bench_gemm_pair.py, K = 512 projections of the
+  // step): time = fixed + rounds * per-round cost * K/512, rounds = ceil(work units / resident CTAs or clusters).
+  //   single CTA, 128x128 tiles : 5.5 us + 2.7 us per round      single CTA, 128x256 : 5.5 us + 3.6 us per round
+  //   CTA pair, 256x256 tiles   : 7.3 us + 2.8 us per round (cluster launch + two cluster syncs cost ~1.8 us)
+  // Split-K launches (weight gradients) take the pair kernel once they fill >= 48 of the 74 clusters.
   const int tiles_m = ceil_div(M, BM);
   const int sms = num_sms();
+  const bool n256 = (N % 256 == 0);
   int bn = 128;
-  if (split_k == 1 && N % 256 == 0) {
-    const int w128 = ceil_div(tiles_m * ceil_div(N, 128), sms);
-    const int w256 = 2 * ceil_div(tiles_m * ceil_div(N, 256), sms);
-    if (w256 <= w128) bn = 256;
+  bool pair = false;
+  if (split_k == 1) {
+    const float kf = (float)K / 512.f;
+    const float t128 = 5.5f + 2.7f * kf * ceil_div(tiles_m * ceil_div(N, 128), sms);
+    const float t256 = n256 ? 5.5f + 3.6f * kf * ceil_div(tiles_m * (N / 256), sms) : 1e30f;
+    const float tpair = (n256 && M >= 2 * BM) ? 7.3f + 2.8f * kf * ceil_div(ceil_div(M, 2 * BM) * (N / 256), sms / 2) : 1e30f;
+    if (t256 < t128) bn = 256;
+    pair = tpair < (t256 < t128 ? t256 : t128);
+  } else {
+    pair = n256 && M >= 2 * BM && ceil_div(M, 2 * BM) * (N / PAIR_BN) * split_k >= 48;
   }
   if (const char* e = getenv("MMNAS_GEMM_BN")) {        // tuning / A-B experiments only
     const int forced = atoi(e);
-    if (forced == 128 || (forced == 256 && split_k == 1 && N % 256 == 0)) bn = forced;
+    if (forced == 128 || (forced == 256 && split_k == 1 && n256)) bn = forced;
   }
-  CUtensorMap ta, tb;
+  if (const char* e = getenv("MMNAS_GEMM_PAIR")) {      // tuning / A-B experiments only: 0 = never, 1 = whenever legal
+    pair = atoi(e) != 0 && n256 && M >= 2 * BM;
+  }
+  if (pair) bn = PAIR_BN / 2;                           // rows of B each CTA stages
+  CUtensorMap ta, tb, tc;
   int rc;
+  // output boxes of 32 rows x 128 bytes: 64 bf16 or 32 fp32 columns
+  rc = out_bf16 ? encode_2d(&tc, C, N, M, ldc, 64, 32) : encode_2d_f32(&tc, C, N, M, ldc, 32, 32);
+  if (rc) return rc;
   if (!a_mn_major) rc = encode_2d(&ta, A, K, M, lda, BK, BM);     // [M rows][K contiguous]
   else rc = encode_2d(&ta, A, M, K, lda, 64, BK);                 // [K rows][M contiguous]
   if (rc) return rc;
@@ -346,7 +599,10 @@ extern "C" int mmnas_gemm_bf16(int M, int N, int K, const void* A, long lda, int
   ep.drop.state = rng_state; ep.drop.salt = salt;
   ep.drop.thresh = (unsigned)(p * 65536.f + 0.5f); ep.drop.scale = p < 1.f ? 1.f / (1.f - p) : 0.f;
   ep.tiles_m = tiles_m; ep.tiles_n = ceil_div(N, bn); ep.kb_total = kb_total; ep.kb_per = kb_per;
+  if (pair) { ep.tiles_m = ceil_div(M, 2 * BM); ep.tiles_n = N / PAIR_BN; }
+  if (const char* e = getenv("MMNAS_GEMM_DEBUG")) ep.debug = atoi(e);
   cudaStream_t s = (cudaStream_t)stream;
-  if (bn == 256) return dispatch<256>(a_mn_major, b_mn_major, ta, tb, ep, s);
-  return dispatch<128>(a_mn_major, b_mn_major, ta, tb, ep, s);
+  if (pair) return dispatch_pair(a_mn_major, b_mn_major, ta, tb, tc, ep, s);
+  if (bn == 256) return dispatch<256>(a_mn_major, b_mn_major, ta, tb, tc, ep, s);
+  return dispatch<128>(a_mn_major, b_mn_major, ta, tb, tc, ep, s);
 }

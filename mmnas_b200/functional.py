@@ -35,11 +35,18 @@ class BlockCfg:
 
 
 def _split_k(M, N, K):
-    """Split the token reduction of a weight-gradient GEMM so that (#output tiles x splits) ~ one wave of 148
-    SMs, keeping at least 4 k-blocks of 64 per split."""
-    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    """Split the token reduction of a weight-gradient GEMM so that (#output tiles x splits) ~ one wave of the GPU,
+    keeping at least 4 k-blocks of 64 per split.  Large outputs with a long reduction go to the CTA-pair kernel
+    (256 x 256 tiles, 74 clusters; the library switches to it at >= 48 units), everything else to 128 x 128 tiles on
+    148 SMs — measured in scripts/bench_gemm_pair.py."""
     kb = (K + 63) // 64
-    return max(1, min(148 // tiles if tiles <= 148 else 1, kb // 4 if kb >= 4 else 1))
+    cap = kb // 4 if kb >= 4 else 1
+    if N % 256 == 0 and M >= 256 and K >= 2048:
+        units = ((M + 255) // 256) * (N // 256)
+        if 8 <= units <= 74:
+            return max(1, min(74 // units, cap))
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    return max(1, min(148 // tiles if tiles <= 148 else 1, cap))
 
 
 def _empty(shape, dtype, dev):

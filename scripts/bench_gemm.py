@@ -30,3 +30,26 @@ os.environ.pop('MMNAS_GEMM_BN')
 for (M, N, Kd, sk) in [(512, 512, 6400, 9), (2048, 512, 6400, 2), (512, 2048, 6400, 2), (1536, 512, 6400, 3), (512, 512, 6400, 4), (512,512,6400,18)]:
     us, tf = run(M, N, Kd, 1, 1, 0, False, sk)
     print('wgrad %4dx%4dx%4d sk%d : %7.1f us %7.1f TF/s' % (M, N, Kd, sk, us, tf))
+
+# library reference on the same shapes (torch.matmul -> cuBLASLt), for DESIGN.md's headroom table only
+def lib(M, N, Kd, iters=20, wgrad=False):
+    if wgrad:
+        A = torch.randn(Kd, M, device=dev).bfloat16(); B = torch.randn(Kd, N, device=dev).bfloat16()
+        f = lambda: torch.matmul(A.t(), B)
+    else:
+        A = torch.randn(M, Kd, device=dev).bfloat16(); B = torch.randn(N, Kd, device=dev).bfloat16()
+        f = lambda: torch.matmul(A, B.t())
+    for _ in range(3): f()
+    torch.cuda.synchronize(); torch.cuda._sleep(int(4e7))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters): f()
+    e1.record(); torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / iters
+    return us, 2.0 * M * N * Kd / us / 1e6
+for (M, N, Kd) in [(6400, 512, 512), (6400, 512, 2048), (6400, 2048, 512), (6400, 1536, 512), (896, 512, 512), (896, 1536, 512), (896, 2048, 512)]:
+    us, tf = lib(M, N, Kd)
+    print('cublas %5dx%4dx%4d : %7.1f us %7.1f TF/s' % (M, N, Kd, us, tf))
+for (M, N, Kd) in [(512, 512, 6400), (2048, 512, 6400), (1536, 512, 6400), (512, 2048, 6400)]:
+    us, tf = lib(M, N, Kd, wgrad=True)
+    print('cublas wgrad %4dx%4dx%4d : %7.1f us %7.1f TF/s' % (M, N, Kd, us, tf))

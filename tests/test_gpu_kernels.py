@@ -68,6 +68,60 @@ def test_gemm_bf16_layouts(a_mn, b_mn, M, N, K_):
     assert normwise(C3, ref) < 1e-5
 
 
+@pytest.mark.parametrize('a_mn,b_mn', [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize('M,N,K_', [(256, 256, 64), (1000, 512, 512), (6400, 256, 192), (300, 768, 1000)])
+def test_gemm_bf16_cta_pair_path(a_mn, b_mn, M, N, K_, monkeypatch):
+    """The cta_group::2 kernel (256x256 tiles over two CTAs) on every operand layout, ragged M (second CTA of the last
+    pair partly / fully out of range), several tiles per cluster (accumulator double buffering), split-K."""
+    monkeypatch.setenv('MMNAS_GEMM_PAIR', '1')
+    k = K()
+    Kp = (K_ + 7) // 8 * 8
+    Mp = (M + 7) // 8 * 8
+    A = rnd(Kp if a_mn else M, Mp if a_mn else Kp, seed=1, dtype=torch.bfloat16)
+    B = rnd(Kp if b_mn else N, N if b_mn else Kp, seed=2, dtype=torch.bfloat16)
+    Ad = (A[:K_, :M].t() if a_mn else A[:, :K_]).double()
+    Bd = (B[:K_] if b_mn else B[:, :K_].t()).double()
+    ref = Ad @ Bd
+    C = torch.full((M, N), float('nan'), device=DEV)
+    k.gemm_bf16(M, N, K_, A, A.stride(0), a_mn, B, B.stride(0), b_mn, C, N)
+    assert normwise(C, ref) < 1e-5
+    monkeypatch.setenv('MMNAS_GEMM_PAIR', '0')
+    C1 = torch.empty(M, N, device=DEV)
+    k.gemm_bf16(M, N, K_, A, A.stride(0), a_mn, B, B.stride(0), b_mn, C1, N)
+    assert torch.equal(C, C1)                       # same products, same K order: the two tilings agree bit for bit
+    monkeypatch.setenv('MMNAS_GEMM_PAIR', '1')
+    C3 = torch.zeros(M, N, device=DEV)
+    k.gemm_bf16(M, N, K_, A, A.stride(0), a_mn, B, B.stride(0), b_mn, C3, N, split_k=3)
+    assert normwise(C3, ref) < 1e-5
+
+
+def test_gemm_bf16_cta_pair_epilogues(monkeypatch):
+    monkeypatch.setenv('MMNAS_GEMM_PAIR', '1')
+    k = K()
+    M, N, K_ = 2000, 512, 512
+    A = rnd(M, K_, seed=1, dtype=torch.bfloat16)
+    B = rnd(N, K_, seed=2, dtype=torch.bfloat16)
+    bias = rnd(N, seed=3)
+    ref = A.double() @ B.double().t()
+    out16 = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    k.gemm_bf16(M, N, K_, A, K_, 0, B, K_, 0, out16, N, bias=bias, relu=True)
+    assert normwise(out16, torch.relu(ref + bias.double())) < 6e-3
+    aux = rnd(M, N, seed=4, dtype=torch.bfloat16)
+    k.gemm_bf16(M, N, K_, A, K_, 0, B, K_, 0, out16, N, aux=aux, ld_aux=N, aux_scale=0.5)
+    assert normwise(out16, torch.where(aux.double() > 0, ref * 0.5, torch.zeros_like(ref))) < 6e-3
+    C = rnd(M, N, seed=5)
+    ref_acc = C.double() + ref
+    k.gemm_bf16(M, N, K_, A, K_, 0, B, K_, 0, C, N, accumulate=True)
+    assert normwise(C, ref_acc) < 1e-5
+    st = torch.tensor([1234, 7], dtype=torch.int64, device=DEV)
+    d = k.Drop(st, salt=99, p=0.1)
+    o1, o2 = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
+    k.gemm_bf16(M, N, K_, A, K_, 0, B, K_, 0, o1, N, drop=d)
+    monkeypatch.setenv('MMNAS_GEMM_PAIR', '0')
+    k.gemm_bf16(M, N, K_, A, K_, 0, B, K_, 0, o2, N, drop=d)
+    assert torch.equal(o1, o2)                      # same dropout mask from either tiling
+
+
 def test_gemm_bf16_epilogues():
     k = K()
     M, N, K_ = 333, 256, 512
