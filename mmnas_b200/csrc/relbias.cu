@@ -6,14 +6,17 @@
 // Backward accumulates dW_r, db_r (and dW_y, db_y in geometry mode; d rel_embed in dense mode) from
 // dbias = dS of the attention backward.
 //
-// Design (v2).  The layer weights (<= 5.5 KB) are staged into __constant__ memory per call, so the fully
-// unrolled per-pair MLP uses FFMA with constant-bank operands: no weight loads at all.  Forward: one thread per
-// (i,j) pair, no shared memory.  Backward: 128-pair tiles; phase A (thread = pair) recomputes e, r and the
-// chain rule and parks e / d pre_e transposed in shared memory ([c][pair], padded so both the scalar writes of
-// phase A and the 128-bit reads of phase B are bank-conflict free); phase B (thread = column c, two half-tiles)
-// reduces the tile into 13 register accumulators per thread (dW_r[:,c], dW_y[c,:], db_y[c]) with a two-level
-// sum; one global atomic per output per CTA at the end.  Persistent grid of 3 CTAs per SM.
-// The constant staging makes these entry points single-stream per device (calls are stream-ordered).
+// Design (v3).  Plain fp32 on the CUDA cores (both precision arms share it; the geometry path is too
+// ill-conditioned for bf16 operands), organised so that the FP32 pipe, not instruction issue, is the limit:
+//  * every multiply-add is a packed FFMA2 (fma.rn.f32x2, two IEEE fp32 FMAs per issue slot);
+//  * the layer weights live in shared memory as ready-made pairs, staged by each CTA from the parameter tensors
+//    (no constant-bank staging copies, so the entry points are stream-safe);
+//  * forward: one thread per TWO pairs, FFMA2 packed over neighbouring rel channels (c, c+1);
+//  * backward: 128-pair tiles.  Phase A (thread = pair, packed over channels) recomputes e and r and parks e
+//    (transposed, padded) plus d pre_r / g (transposed) in shared memory.  Phase B (thread = channel c over half
+//    of the tile, packed over neighbouring PAIRS) forms d e = W_r[:,c] . d pre_r with its own weight column in
+//    registers and reduces dW_r[:,c], dW_y[c,:], db_y[c] with a two-level sum; one global atomic per output per
+//    CTA at the end.  44 KB of shared memory per CTA, persistent grid of 4 CTAs per SM.
 #include "common.cuh"
 #include "../../include/mmnas_b200.h"
 
@@ -21,170 +24,267 @@ namespace {
 
 constexpr int MAXH = 16;     // heads
 constexpr int R = 64;        // REL_SIZE
-constexpr int TILE = 128;    // pairs per tile == threads per CTA
+constexpr int R2 = R / 2;    // channel pairs
+constexpr int TILE = 128;    // pairs per backward tile == threads per CTA
 constexpr int EP = TILE + 4; // padded pair pitch of the transposed tiles
 
-__constant__ float cWy[R * 4];
-__constant__ float cby[R];
-__constant__ float cWr[MAXH * R];
-__constant__ float cbr[MAXH];
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+  u64 d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ void unpk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ float sum2(u64 v) {
+  float lo, hi;
+  unpk2(v, lo, hi);
+  return lo + hi;
+}
 
 struct RelArgs {
   int B, N, heads;
   unsigned pairs, nn;
   const float* rel;     // dense: [pairs, R]
   const float* g4;      // geometry: [pairs, 4]
+  const float *Wy, *by, *Wr, *br;
   float* bias;          // [B, heads, N, N]
   const float* dbias;
   float* drel;
   float *dWy, *dby, *dWr, *dbr;
 };
 
+// shared-memory weights, as channel pairs: Wy2[c2][k] = (Wy[2c2][k], Wy[2c2+1][k]), by2[c2], Wr2[c2][h] =
+// (Wr[h][2c2], Wr[h][2c2+1]), then br[h]
+template <int HEADS> constexpr int sw_floats() { return 2 * (R2 * 4 + R2 + R2 * HEADS) + MAXH; }
+
 template <int HEADS, bool DENSE>
-__global__ void __launch_bounds__(256) relbias_fwd_kernel(RelArgs a) {
-  pdl_wait(); pdl_launch();
-  const unsigned pair = blockIdx.x * 256u + threadIdx.x;
-  if (pair >= a.pairs) return;
-  float r[HEADS];
-#pragma unroll
-  for (int h = 0; h < HEADS; ++h) r[h] = cbr[h];
-  if (DENSE) {
-    const float4* e4 = reinterpret_cast<const float4*>(a.rel + (size_t)pair * R);
-#pragma unroll
-    for (int c4 = 0; c4 < R / 4; ++c4) {
-      const float4 e = __ldg(e4 + c4);
-#pragma unroll
-      for (int h = 0; h < HEADS; ++h) {
-        r[h] = fmaf(cWr[h * R + 4 * c4 + 0], e.x, r[h]);
-        r[h] = fmaf(cWr[h * R + 4 * c4 + 1], e.y, r[h]);
-        r[h] = fmaf(cWr[h * R + 4 * c4 + 2], e.z, r[h]);
-        r[h] = fmaf(cWr[h * R + 4 * c4 + 3], e.w, r[h]);
-      }
+__device__ __forceinline__ void stage_weights(float* sw, const RelArgs& a, int tid, int nthr) {
+  float2* Wy2 = reinterpret_cast<float2*>(sw);
+  float2* by2 = Wy2 + R2 * 4;
+  float2* Wr2 = by2 + R2;
+  float* br = reinterpret_cast<float*>(Wr2 + R2 * HEADS);
+  if (!DENSE) {
+    for (int i = tid; i < R2 * 4; i += nthr) {
+      const int c2 = i >> 2, k = i & 3;
+      Wy2[i] = make_float2(__ldg(a.Wy + (2 * c2) * 4 + k), __ldg(a.Wy + (2 * c2 + 1) * 4 + k));
     }
-  } else {
-    const float4 g = __ldg(reinterpret_cast<const float4*>(a.g4) + pair);
-#pragma unroll
-    for (int c = 0; c < R; ++c) {
-      const float e = fmaxf(fmaf(cWy[c * 4 + 0], g.x, fmaf(cWy[c * 4 + 1], g.y, fmaf(cWy[c * 4 + 2], g.z, fmaf(cWy[c * 4 + 3], g.w, cby[c])))), 0.f);
-#pragma unroll
-      for (int h = 0; h < HEADS; ++h) r[h] = fmaf(cWr[h * R + c], e, r[h]);
-    }
+    for (int i = tid; i < R2; i += nthr) by2[i] = make_float2(__ldg(a.by + 2 * i), __ldg(a.by + 2 * i + 1));
   }
-  const unsigned b = pair / a.nn, ij = pair - b * a.nn;
-  float* out = a.bias + ((size_t)b * HEADS) * a.nn + ij;
+  for (int i = tid; i < R2 * HEADS; i += nthr) {
+    const int c2 = i / HEADS, h = i - c2 * HEADS;
+    Wr2[i] = make_float2(__ldg(a.Wr + h * R + 2 * c2), __ldg(a.Wr + h * R + 2 * c2 + 1));
+  }
+  for (int i = tid; i < HEADS; i += nthr) br[i] = __ldg(a.br + i);
+}
+
+// e (channel pair c2) and r += W_r e for ONE pair; `gk` = the pair's geometry, each component duplicated
+template <int HEADS>
+__device__ __forceinline__ u64 geo_channel_pair(const u64* Wy2, const u64* by2, const u64 (&gk)[4], int c2) {
+  u64 e2 = by2[c2];
 #pragma unroll
-  for (int h = 0; h < HEADS; ++h) out[(size_t)h * a.nn] = logf(fmaxf(fmaxf(r[h], 0.f), 1e-6f));
+  for (int k = 0; k < 4; ++k) e2 = ffma2(Wy2[c2 * 4 + k], gk[k], e2);
+  float lo, hi;
+  unpk2(e2, lo, hi);
+  return pk2(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
 }
 
 template <int HEADS, bool DENSE>
-__global__ void __launch_bounds__(TILE) relbias_bwd_kernel(RelArgs a) {
-  extern __shared__ float sm[];
-  float* E = sm;                     // [R][EP]   e, transposed
-  float* DE = E + R * EP;            // [R][EP]   d pre_e (geometry) / d rel (dense), transposed
-  float* Dp = DE + R * EP;           // [TILE][HP] d pre_r
-  constexpr int HP = HEADS < 4 ? 4 : HEADS;
-  float* G = Dp + TILE * HP;         // [TILE][4]
+__global__ void __launch_bounds__(256) relbias_fwd_kernel(RelArgs a) {
+  extern __shared__ __align__(16) float sw[];
+  pdl_wait(); pdl_launch();
+  stage_weights<HEADS, DENSE>(sw, a, threadIdx.x, 256);
+  __syncthreads();
+  const u64* Wy2 = reinterpret_cast<const u64*>(sw);
+  const u64* by2 = Wy2 + R2 * 4;
+  const u64* Wr2 = by2 + R2;
+  const float* br = reinterpret_cast<const float*>(Wr2 + R2 * HEADS);
+  const unsigned p0 = 2u * (blockIdx.x * 256u + threadIdx.x), p1 = p0 + 1u;
+  if (p0 >= a.pairs) return;
+  const bool two = p1 < a.pairs;
+  u64 rA[HEADS], rB[HEADS];
+#pragma unroll
+  for (int h = 0; h < HEADS; ++h) rA[h] = rB[h] = pk2(br[h], 0.f);
+  if (DENSE) {
+    const float4* eA = reinterpret_cast<const float4*>(a.rel + (size_t)p0 * R);
+    const float4* eB = reinterpret_cast<const float4*>(a.rel + (size_t)(two ? p1 : p0) * R);
+#pragma unroll 4
+    for (int c4 = 0; c4 < R / 4; ++c4) {
+      const float4 x = __ldg(eA + c4), y = __ldg(eB + c4);
+      const u64 xa = pk2(x.x, x.y), xb = pk2(x.z, x.w), ya = pk2(y.x, y.y), yb = pk2(y.z, y.w);
+#pragma unroll
+      for (int h = 0; h < HEADS; ++h) {
+        const u64 w0 = Wr2[(2 * c4) * HEADS + h], w1 = Wr2[(2 * c4 + 1) * HEADS + h];
+        rA[h] = ffma2(w1, xb, ffma2(w0, xa, rA[h]));
+        rB[h] = ffma2(w1, yb, ffma2(w0, ya, rB[h]));
+      }
+    }
+  } else {
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(a.g4) + p0);
+    const float4 gb = __ldg(reinterpret_cast<const float4*>(a.g4) + (two ? p1 : p0));
+    const u64 gA[4] = {pk2(ga.x, ga.x), pk2(ga.y, ga.y), pk2(ga.z, ga.z), pk2(ga.w, ga.w)};
+    const u64 gB[4] = {pk2(gb.x, gb.x), pk2(gb.y, gb.y), pk2(gb.z, gb.z), pk2(gb.w, gb.w)};
+#pragma unroll 4
+    for (int c2 = 0; c2 < R2; ++c2) {
+      const u64 eA = geo_channel_pair<HEADS>(Wy2, by2, gA, c2);
+      const u64 eB = geo_channel_pair<HEADS>(Wy2, by2, gB, c2);
+#pragma unroll
+      for (int h = 0; h < HEADS; ++h) {
+        const u64 w = Wr2[c2 * HEADS + h];
+        rA[h] = ffma2(w, eA, rA[h]);
+        rB[h] = ffma2(w, eB, rB[h]);
+      }
+    }
+  }
+  const unsigned b0 = p0 / a.nn, ij0 = p0 - b0 * a.nn;
+  float* o0 = a.bias + ((size_t)b0 * HEADS) * a.nn + ij0;
+  if (two && ij0 + 1u < a.nn && (a.nn & 1u) == 0u) {      // both pairs in one image, 8-byte aligned: one store per head
+#pragma unroll
+    for (int h = 0; h < HEADS; ++h)
+      *reinterpret_cast<float2*>(o0 + (size_t)h * a.nn) =
+          make_float2(logf(fmaxf(fmaxf(sum2(rA[h]), 0.f), 1e-6f)), logf(fmaxf(fmaxf(sum2(rB[h]), 0.f), 1e-6f)));
+  } else {
+#pragma unroll
+    for (int h = 0; h < HEADS; ++h) o0[(size_t)h * a.nn] = logf(fmaxf(fmaxf(sum2(rA[h]), 0.f), 1e-6f));
+    if (two) {
+      const unsigned b1 = p1 / a.nn, ij1 = p1 - b1 * a.nn;
+      float* o1 = a.bias + ((size_t)b1 * HEADS) * a.nn + ij1;
+#pragma unroll
+      for (int h = 0; h < HEADS; ++h) o1[(size_t)h * a.nn] = logf(fmaxf(fmaxf(sum2(rB[h]), 0.f), 1e-6f));
+    }
+  }
+}
+
+template <int HEADS, bool DENSE>
+__global__ void __launch_bounds__(TILE, 4) relbias_bwd_kernel(RelArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  float* E = sm;                          // [R][EP]      e, transposed
+  float* DpT = E + R * EP;                // [HEADS][EP]  d pre_r, transposed
+  float* GT = DpT + HEADS * EP;           // [4][EP]      geometry, transposed
+  float* sw = GT + 4 * EP;
   pdl_wait(); pdl_launch();
   const int t = threadIdx.x;
-  const int c_own = t & 63, half = t >> 6;      // phase B: column and which half of the tile's pairs
+  stage_weights<HEADS, DENSE>(sw, a, t, TILE);
+  const u64* Wy2 = reinterpret_cast<const u64*>(sw);
+  const u64* by2 = Wy2 + R2 * 4;
+  const u64* Wr2 = by2 + R2;
+  const float* br = reinterpret_cast<const float*>(Wr2 + R2 * HEADS);
+  const int c_own = t & 63, half = t >> 6;      // phase B: channel and which half of the tile's pairs
+  u64 wcol[HEADS];                              // W_r[:, c_own], duplicated
+#pragma unroll
+  for (int h = 0; h < HEADS; ++h) {
+    const float w = __ldg(a.Wr + h * R + c_own);
+    wcol[h] = pk2(w, w);
+  }
+  const u64 one2 = pk2(1.f, 1.f);
   float accWr[HEADS], accWy[4] = {0.f, 0.f, 0.f, 0.f}, accby = 0.f, accbr = 0.f;
 #pragma unroll
   for (int h = 0; h < HEADS; ++h) accWr[h] = 0.f;
   const unsigned ntiles = (a.pairs + TILE - 1) / TILE;
   for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    __syncthreads();
-    // ---------------- phase A: thread = pair
+    __syncthreads();                            // weights staged / previous tile fully consumed
+    // ---------------- phase A: thread = pair, packed over channel pairs
     const unsigned pair = tile * TILE + t;
     const bool live = pair < a.pairs;
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    float r[HEADS];
-#pragma unroll
-    for (int h = 0; h < HEADS; ++h) r[h] = cbr[h];
-    if (DENSE) {
-      const float4* e4 = reinterpret_cast<const float4*>(a.rel + (size_t)pair * R);
-#pragma unroll
-      for (int c4 = 0; c4 < R / 4; ++c4) {
-        const float4 e = live ? __ldg(e4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        E[(4 * c4 + 0) * EP + t] = e.x; E[(4 * c4 + 1) * EP + t] = e.y;
-        E[(4 * c4 + 2) * EP + t] = e.z; E[(4 * c4 + 3) * EP + t] = e.w;
-#pragma unroll
-        for (int h = 0; h < HEADS; ++h) {
-          r[h] = fmaf(cWr[h * R + 4 * c4 + 0], e.x, r[h]);
-          r[h] = fmaf(cWr[h * R + 4 * c4 + 1], e.y, r[h]);
-          r[h] = fmaf(cWr[h * R + 4 * c4 + 2], e.z, r[h]);
-          r[h] = fmaf(cWr[h * R + 4 * c4 + 3], e.w, r[h]);
-        }
-      }
-    } else {
-      if (live) g = __ldg(reinterpret_cast<const float4*>(a.g4) + pair);
-#pragma unroll
-      for (int c = 0; c < R; ++c) {
-        float e = fmaxf(fmaf(cWy[c * 4 + 0], g.x, fmaf(cWy[c * 4 + 1], g.y, fmaf(cWy[c * 4 + 2], g.z, fmaf(cWy[c * 4 + 3], g.w, cby[c])))), 0.f);
-        e = live ? e : 0.f;
-        E[c * EP + t] = e;
-#pragma unroll
-        for (int h = 0; h < HEADS; ++h) r[h] = fmaf(cWr[h * R + c], e, r[h]);
-      }
-      *reinterpret_cast<float4*>(G + t * 4) = g;
-    }
-    float dpre[HEADS];
+    float db[HEADS];                            // issued first: their latency hides behind the channel loop
     {
       const unsigned b = live ? pair / a.nn : 0u, ij = live ? pair - b * a.nn : 0u;
-      const float* db = a.dbias + ((size_t)b * HEADS) * a.nn + ij;
+      const float* dbp = a.dbias + ((size_t)b * HEADS) * a.nn + ij;
 #pragma unroll
-      for (int h = 0; h < HEADS; ++h) {
-        dpre[h] = (live && r[h] > 1e-6f) ? __ldg(db + (size_t)h * a.nn) / r[h] : 0.f;   // relu and clamp both pass
-        Dp[t * HP + h] = dpre[h];
+      for (int h = 0; h < HEADS; ++h) db[h] = live ? __ldg(dbp + (size_t)h * a.nn) : 0.f;
+    }
+    u64 r2[HEADS];
+#pragma unroll
+    for (int h = 0; h < HEADS; ++h) r2[h] = pk2(br[h], 0.f);
+    if (DENSE) {
+      const float4* e4 = reinterpret_cast<const float4*>(a.rel + (size_t)(live ? pair : 0u) * R);
+#pragma unroll 4
+      for (int c4 = 0; c4 < R / 4; ++c4) {
+        float4 e = __ldg(e4 + c4);
+        if (!live) e = make_float4(0.f, 0.f, 0.f, 0.f);
+        E[(4 * c4 + 0) * EP + t] = e.x; E[(4 * c4 + 1) * EP + t] = e.y;
+        E[(4 * c4 + 2) * EP + t] = e.z; E[(4 * c4 + 3) * EP + t] = e.w;
+        const u64 ea = pk2(e.x, e.y), eb = pk2(e.z, e.w);
+#pragma unroll
+        for (int h = 0; h < HEADS; ++h)
+          r2[h] = ffma2(Wr2[(2 * c4 + 1) * HEADS + h], eb, ffma2(Wr2[(2 * c4) * HEADS + h], ea, r2[h]));
+      }
+    } else {
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) g = __ldg(reinterpret_cast<const float4*>(a.g4) + pair);
+      GT[0 * EP + t] = g.x; GT[1 * EP + t] = g.y; GT[2 * EP + t] = g.z; GT[3 * EP + t] = g.w;
+      const u64 gk[4] = {pk2(g.x, g.x), pk2(g.y, g.y), pk2(g.z, g.z), pk2(g.w, g.w)};
+#pragma unroll 4
+      for (int c2 = 0; c2 < R2; ++c2) {
+        u64 e2 = geo_channel_pair<HEADS>(Wy2, by2, gk, c2);
+        float lo, hi;
+        unpk2(e2, lo, hi);
+        if (!live) { lo = hi = 0.f; e2 = 0ull; }
+        E[(2 * c2) * EP + t] = lo;
+        E[(2 * c2 + 1) * EP + t] = hi;
+#pragma unroll
+        for (int h = 0; h < HEADS; ++h) r2[h] = ffma2(Wr2[c2 * HEADS + h], e2, r2[h]);
       }
     }
 #pragma unroll
-    for (int c = 0; c < R; ++c) {
-      float de = 0.f;
-#pragma unroll
-      for (int h = 0; h < HEADS; ++h) de = fmaf(cWr[h * R + c], dpre[h], de);
-      if (!DENSE) de = E[c * EP + t] > 0.f ? de : 0.f;
-      DE[c * EP + t] = de;
+    for (int h = 0; h < HEADS; ++h) {
+      const float r = sum2(r2[h]);
+      DpT[h * EP + t] = (live && r > 1e-6f) ? __fdividef(db[h], r) : 0.f;     // relu and clamp both pass
     }
     __syncthreads();
-    if (DENSE && live) {      // d rel_embed row of this pair
-      float4* o4 = reinterpret_cast<float4*>(a.drel + (size_t)pair * R);
+    // ---------------- phase B: thread = channel c_own over its half of the pairs, packed over pair pairs
+    u64 pWr[HEADS], pWy[4] = {0ull, 0ull, 0ull, 0ull}, pby = 0ull;
+    float pbr = 0.f;
 #pragma unroll
-      for (int c4 = 0; c4 < R / 4; ++c4)
-        o4[c4] = make_float4(DE[(4 * c4 + 0) * EP + t], DE[(4 * c4 + 1) * EP + t], DE[(4 * c4 + 2) * EP + t],
-                             DE[(4 * c4 + 3) * EP + t]);
-    }
-    // ---------------- phase B: thread = column c_own over its half of the pairs; two-level summation
-    float pWr[HEADS], pWy[4] = {0.f, 0.f, 0.f, 0.f}, pby = 0.f, pbr = 0.f;
-#pragma unroll
-    for (int h = 0; h < HEADS; ++h) pWr[h] = 0.f;
+    for (int h = 0; h < HEADS; ++h) pWr[h] = 0ull;
     const int p0 = half * (TILE / 2);
 #pragma unroll 2
     for (int p = p0; p < p0 + TILE / 2; p += 4) {
       const float4 ev = *reinterpret_cast<const float4*>(E + c_own * EP + p);
-      const float ee[4] = {ev.x, ev.y, ev.z, ev.w};
-      float dd[4] = {0.f, 0.f, 0.f, 0.f};
-      if (!DENSE) {
-        const float4 dv = *reinterpret_cast<const float4*>(DE + c_own * EP + p);
-        dd[0] = dv.x; dd[1] = dv.y; dd[2] = dv.z; dd[3] = dv.w;
+      const u64 ea = pk2(ev.x, ev.y), eb = pk2(ev.z, ev.w);
+      u64 da = 0ull, dbq = 0ull;
+#pragma unroll
+      for (int h = 0; h < HEADS; ++h) {
+        const float4 dv = *reinterpret_cast<const float4*>(DpT + h * EP + p);     // same address in every lane
+        const u64 dpa = pk2(dv.x, dv.y), dpb = pk2(dv.z, dv.w);
+        da = ffma2(wcol[h], dpa, da);
+        dbq = ffma2(wcol[h], dpb, dbq);
+        pWr[h] = ffma2(dpb, eb, ffma2(dpa, ea, pWr[h]));
       }
+      if (DENSE) {            // d rel_embed[pair][c]: lanes = 32 consecutive channels of one pair
+        float d0, d1, d2, d3;
+        unpk2(da, d0, d1); unpk2(dbq, d2, d3);
+        const size_t base = (size_t)tile * TILE + p;
+        if (base + 0 < a.pairs) a.drel[(base + 0) * R + c_own] = d0;
+        if (base + 1 < a.pairs) a.drel[(base + 1) * R + c_own] = d1;
+        if (base + 2 < a.pairs) a.drel[(base + 2) * R + c_own] = d2;
+        if (base + 3 < a.pairs) a.drel[(base + 3) * R + c_own] = d3;
+      } else {
+        float d0, d1, d2, d3;
+        unpk2(da, d0, d1); unpk2(dbq, d2, d3);
+        da = pk2(ev.x > 0.f ? d0 : 0.f, ev.y > 0.f ? d1 : 0.f);                   // through the relu of linear_y_rel
+        dbq = pk2(ev.z > 0.f ? d2 : 0.f, ev.w > 0.f ? d3 : 0.f);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-#pragma unroll
-        for (int h = 0; h < HEADS; ++h) pWr[h] = fmaf(Dp[(p + u) * HP + h], ee[u], pWr[h]);
-        if (!DENSE) {
-          const float4 gv = *reinterpret_cast<const float4*>(G + (p + u) * 4);
-          pWy[0] = fmaf(dd[u], gv.x, pWy[0]); pWy[1] = fmaf(dd[u], gv.y, pWy[1]);
-          pWy[2] = fmaf(dd[u], gv.z, pWy[2]); pWy[3] = fmaf(dd[u], gv.w, pWy[3]);
-          pby += dd[u];
+        for (int k = 0; k < 4; ++k) {
+          const float4 gv = *reinterpret_cast<const float4*>(GT + k * EP + p);
+          pWy[k] = ffma2(dbq, pk2(gv.z, gv.w), ffma2(da, pk2(gv.x, gv.y), pWy[k]));
         }
-        if (c_own < HEADS) pbr += Dp[(p + u) * HP + c_own];
+        pby = ffma2(dbq, one2, ffma2(da, one2, pby));
+      }
+      if (c_own < HEADS) {
+        const float4 dv = *reinterpret_cast<const float4*>(DpT + c_own * EP + p);
+        pbr += (dv.x + dv.y) + (dv.z + dv.w);
       }
     }
 #pragma unroll
-    for (int h = 0; h < HEADS; ++h) accWr[h] += pWr[h];
+    for (int h = 0; h < HEADS; ++h) accWr[h] += sum2(pWr[h]);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) accWy[k] += pWy[k];
-    accby += pby; accbr += pbr;
+    for (int k = 0; k < 4; ++k) accWy[k] += sum2(pWy[k]);
+    accby += sum2(pby); accbr += pbr;
   }
 #pragma unroll
   for (int h = 0; h < HEADS; ++h) atomicAdd(&a.dWr[h * R + c_own], accWr[h]);
@@ -198,7 +298,7 @@ __global__ void __launch_bounds__(TILE) relbias_bwd_kernel(RelArgs a) {
 
 template <int HEADS>
 constexpr size_t bwd_smem_bytes() {
-  return sizeof(float) * (2 * R * EP + TILE * (HEADS < 4 ? 4 : HEADS) + TILE * 4);
+  return sizeof(float) * (R * EP + HEADS * EP + 4 * EP + sw_floats<HEADS>());
 }
 
 int check(int B, int N, int heads, int Rin, const float* rel, const float* g4, const float* Wy, const float* by,
@@ -213,21 +313,12 @@ int check(int B, int N, int heads, int Rin, const float* rel, const float* g4, c
   return MMNAS_OK;
 }
 
-int stage_weights(int heads, const float* Wy, const float* by, const float* Wr, const float* br, cudaStream_t s) {
-  if (Wy) {
-    MMNAS_CUDA(cudaMemcpyToSymbolAsync(cWy, Wy, sizeof(float) * R * 4, 0, cudaMemcpyDeviceToDevice, s));
-    MMNAS_CUDA(cudaMemcpyToSymbolAsync(cby, by, sizeof(float) * R, 0, cudaMemcpyDeviceToDevice, s));
-  }
-  MMNAS_CUDA(cudaMemcpyToSymbolAsync(cWr, Wr, sizeof(float) * heads * R, 0, cudaMemcpyDeviceToDevice, s));
-  MMNAS_CUDA(cudaMemcpyToSymbolAsync(cbr, br, sizeof(float) * heads, 0, cudaMemcpyDeviceToDevice, s));
-  return MMNAS_OK;
-}
-
 template <int HEADS>
 int launch_fwd(const RelArgs& a, cudaStream_t s) {
-  const unsigned grid = (a.pairs + 255u) / 256u;
-  if (a.rel) MMNAS_CUDA(mmnas_launch(relbias_fwd_kernel<HEADS, true>, dim3(grid), dim3(256), 0, s, a));
-  else MMNAS_CUDA(mmnas_launch(relbias_fwd_kernel<HEADS, false>, dim3(grid), dim3(256), 0, s, a));
+  const unsigned grid = (a.pairs + 511u) / 512u;             // two pairs per thread
+  constexpr size_t smem = sizeof(float) * sw_floats<HEADS>();
+  if (a.rel) MMNAS_CUDA(mmnas_launch(relbias_fwd_kernel<HEADS, true>, dim3(grid), dim3(256), smem, s, a));
+  else MMNAS_CUDA(mmnas_launch(relbias_fwd_kernel<HEADS, false>, dim3(grid), dim3(256), smem, s, a));
   return MMNAS_OK;
 }
 
@@ -241,7 +332,7 @@ int launch_bwd(const RelArgs& a, cudaStream_t s) {
     attr_done = true;
   }
   const unsigned ntiles = (a.pairs + TILE - 1) / TILE;
-  const unsigned grid = ntiles < 148u * 3u ? ntiles : 148u * 3u;
+  const unsigned grid = ntiles < 148u * 4u ? ntiles : 148u * 4u;
   if (a.rel) MMNAS_CUDA(mmnas_launch(relbias_bwd_kernel<HEADS, true>, dim3(grid), dim3(TILE), smem, s, a));
   else MMNAS_CUDA(mmnas_launch(relbias_bwd_kernel<HEADS, false>, dim3(grid), dim3(TILE), smem, s, a));
   return MMNAS_OK;
@@ -266,11 +357,9 @@ extern "C" int mmnas_relbias_fwd(int B, int N, int heads, int Rin, const float* 
   if (B == 0) return MMNAS_OK;
   MMNAS_CHECK_ARG(bias, "relbias_fwd: null output");
   cudaStream_t s = (cudaStream_t)stream;
-  rc = stage_weights(heads, g4 ? Wy : nullptr, by, Wr, br, s);
-  if (rc) return rc;
   RelArgs a = {};
   a.B = B; a.N = N; a.heads = heads; a.nn = (unsigned)N * N; a.pairs = (unsigned)B * a.nn;
-  a.rel = rel; a.g4 = g4; a.bias = bias;
+  a.rel = rel; a.g4 = g4; a.Wy = Wy; a.by = by; a.Wr = Wr; a.br = br; a.bias = bias;
   DISPATCH_HEADS(launch_fwd, heads, a, s)
 }
 
@@ -284,10 +373,8 @@ extern "C" int mmnas_relbias_bwd(int B, int N, int heads, int Rin, const float* 
   MMNAS_CHECK_ARG(!rel || drel, "relbias_bwd: dense mode needs d rel_embed output");
   MMNAS_CHECK_ARG(!g4 || (dWy && dby), "relbias_bwd: geometry mode needs dWy/dby outputs");
   cudaStream_t s = (cudaStream_t)stream;
-  rc = stage_weights(heads, g4 ? Wy : nullptr, by, Wr, br, s);
-  if (rc) return rc;
   RelArgs a = {};
   a.B = B; a.N = N; a.heads = heads; a.nn = (unsigned)N * N; a.pairs = (unsigned)B * a.nn;
-  a.rel = rel; a.g4 = g4; a.dbias = dbias; a.drel = drel; a.dWy = dWy; a.dby = dby; a.dWr = dWr; a.dbr = dbr;
+  a.rel = rel; a.g4 = g4; a.Wy = Wy; a.by = by; a.Wr = Wr; a.br = br; a.dbias = dbias; a.drel = drel; a.dWy = dWy; a.dby = dby; a.dWr = dWr; a.dbr = dbr;
   DISPATCH_HEADS(launch_bwd, heads, a, s)
 }
