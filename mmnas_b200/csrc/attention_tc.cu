@@ -1,7 +1,11 @@
 // Attention core on the 5th-gen tensor cores (bf16 arm).  One CTA (128 threads) per (sample, head):
 //   forward   S = Q K^T          (tcgen05.mma 128 x N1 x 64, accumulator in TMEM columns [0,128))
 //             softmax: thread i owns query row i == TMEM lane i, so row max / sum are thread-local (no shuffles);
-//             the whole row of logits stays in registers (TMEM is read once)
+//             the logits are re-read from TMEM in 32-column chunks by rolled loops (max pass, exp/sum pass): a
+//             register-resident row needed 196 registers and 150-214 KB of straight-line code, which ran at the
+//             speed of instruction-cache misses (ncu: 45 % of stalls no_instruction); chunked code is ~6x smaller,
+//             fits 128 registers and lets the forward run four CTAs per SM (P aliases the dead Q/K tiles, O the
+//             dead S columns), i.e. all 512 (sample, head) CTAs of a launch in one wave
 //             P (bf16, dropout applied) -> shared memory in the canonical K-major 128B-swizzled UMMA layout
 //             O = P V            (A = P K-major, B = V as an MN-major operand straight from its TMA tile)
 //   backward  S = Q K^T, dP = dO V^T                       (V's tile re-read as a K-major operand)
@@ -46,35 +50,41 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 
 // Row-resident softmax state of one thread (= one query row = one TMEM lane): up to 4 chunks of 32 logits.
 struct RowCtx {
-  uint32_t mk[4];          // padded-key bitmask, bit t of word c = key 32c+t (warp-uniform)
+  uint32_t mk0, mk1, mk2, mk3;   // padded-key bitmask, bit t of word c = key 32c+t (warp-uniform)
   const float* brow;       // bias row or null
-  bool vec;                // bias / dbias rows are 16-byte aligned (Nk % 4 == 0)
   uint64_t rowbase;        // dropout element index of (row, key 0)
 };
 
 __device__ __forceinline__ RowCtx make_row_ctx(const AttnTcArgs& a, int b, int h, int i, bool row_ok, int lane) {
   RowCtx c;
   const unsigned char* mrow = a.kmask ? a.kmask + (size_t)b * a.Nk : nullptr;
+  uint32_t mk[4];
 #pragma unroll
   for (int w = 0; w < 4; ++w) {
     const int j = w * 32 + lane;
     const bool m = mrow != nullptr && j < a.Nk && mrow[j] != 0;
-    c.mk[w] = __ballot_sync(0xffffffffu, m);
+    mk[w] = __ballot_sync(0xffffffffu, m);
   }
+  c.mk0 = mk[0]; c.mk1 = mk[1]; c.mk2 = mk[2]; c.mk3 = mk[3];
   c.rowbase = (((uint64_t)b * a.heads + h) * a.Nq + i) * a.Nk;
   c.brow = (a.bias && row_ok) ? a.bias + c.rowbase : nullptr;
-  c.vec = (a.Nk & 3) == 0;
   return c;
 }
 
-// logits of chunk cc from the raw accumulator: scale, bias, mask; keys >= Nk -> -inf
+__device__ __forceinline__ uint32_t chunk_mask(const RowCtx& c, int cc) {     // cc is a run-time loop index
+  return cc < 2 ? (cc == 0 ? c.mk0 : c.mk1) : (cc == 2 ? c.mk2 : c.mk3);
+}
+
+// logits of chunk cc from the raw accumulator: scale, bias, mask; keys >= Nk -> -inf.
+// VEC: bias / dbias rows are 16-byte aligned and dropout groups do not straddle rows (Nk % 4 == 0).
+template <bool VEC>
 __device__ __forceinline__ void chunk_logits(const AttnTcArgs& a, const RowCtx& c, int cc, const uint32_t (&r)[32], float (&s)[32]) {
   const int j0 = cc * 32;
   float bb[32];
 #pragma unroll
   for (int t = 0; t < 32; ++t) bb[t] = 0.f;
   if (c.brow) {
-    if (c.vec) {
+    if (VEC) {
 #pragma unroll
       for (int g = 0; g < 8; ++g)
         if (j0 + 4 * g < a.Nk) {
@@ -87,7 +97,7 @@ __device__ __forceinline__ void chunk_logits(const AttnTcArgs& a, const RowCtx& 
         if (j0 + t < a.Nk) bb[t] = __ldg(c.brow + j0 + t);
     }
   }
-  const uint32_t mk = c.mk[cc];
+  const uint32_t mk = chunk_mask(c, cc);
 #pragma unroll
   for (int t = 0; t < 32; ++t) {
     float v = fmaf(__uint_as_float(r[t]), a.scale, bb[t]);
@@ -97,8 +107,9 @@ __device__ __forceinline__ void chunk_logits(const AttnTcArgs& a, const RowCtx& 
 }
 
 // dropout multipliers of 4 consecutive keys j..j+3 (j % 4 == 0) of this row: one hash when the row is 4-aligned
+template <bool VEC>
 __device__ __forceinline__ void drop4(const AttnTcArgs& a, const RowCtx& c, uint64_t key, int j, float (&m)[4]) {
-  if (c.vec) {
+  if (VEC) {
     const uint64_t r = mmnas_mix64(key ^ (((c.rowbase + j) >> 2) * 0x9E3779B97F4A7C15ull));
 #pragma unroll
     for (int u = 0; u < 4; ++u) m[u] = ((unsigned)(r >> (16 * u)) & 0xFFFFu) < a.drop.thresh ? 0.f : a.drop.scale;
@@ -122,21 +133,25 @@ __device__ __forceinline__ void tc_prologue(uint32_t bar_base, int nbars, uint32
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(128, 2)
+template <bool VEC>
+__global__ void __launch_bounds__(128, 4)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                    const __grid_constant__ CUtensorMap tv, AttnTcArgs a) {
+  // Four CTAs per SM: 48 KB of shared memory and 128 TMEM columns each.
+  //   smem: Q | K | V ; P (two 64-wide chunks) overwrites Q | K once S = Q K^T has retired
+  //   TMEM: S [0,128), then O [0,64) once every thread has read its logits
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by POINTER arithmetic on the shared array: an integer round trip loses the address space
   // and every staging access becomes a generic ST.E / LD.E instead of STS / LDS
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const uint32_t sQ = smem_u32(smem), sK = sQ + TILE_BYTES, sV = sK + TILE_BYTES, sP = sV + TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * TILE_BYTES + PTILE_BYTES);
+  const uint32_t sQ = smem_u32(smem), sK = sQ + TILE_BYTES, sV = sK + TILE_BYTES, sP = sQ;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * TILE_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   const uint32_t bar = smem_u32(bars);
   const int h = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int Nq = a.Nq, Nk = a.Nk;
-  tc_prologue(bar, 3, tmem_slot, 256, warp);
+  tc_prologue(bar, 3, tmem_slot, 128, warp);
   pdl_wait();                       // prologue above overlapped the previous kernel's tail
   const uint32_t tmem = *tmem_slot;
   const int n1 = max(16, (Nk + 15) & ~15);            // UMMA N of S = Q K^T
@@ -153,9 +168,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       umma_bf16(tmem, make_smem_desc(sQ + kk * 32, 16, 1024), make_smem_desc(sK + kk * 32, 16, 1024), idesc, kk > 0);
     umma_commit(bar + 8);
   }
-  mbar_wait(bar + 8, 0);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
   const int i = tid;
   const bool row_ok = i < Nq;
   const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
@@ -163,65 +175,69 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   const bool use_drop = a.drop.state != nullptr && a.drop.thresh > 0;
   const uint64_t key = use_drop ? drop_key(a.drop) : 0;
   const RowCtx ctx = make_row_ctx(a, b, h, i, row_ok, tid & 31);
-  float s[4][32];                                   // the whole row stays in registers: TMEM is read once
+  mbar_wait(bar + 8, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  pdl_launch();
+
   float mx = -INFINITY;
+#pragma unroll 1
+  for (int cc = 0; cc < NC; ++cc) {                 // pass 1: row maximum
+    uint32_t r[32];
+    float s[32];
+    tmem_ld32(trow + cc * 32, r);
+    chunk_logits<VEC>(a, ctx, cc, r, s);
 #pragma unroll
-  for (int cc = 0; cc < 4; ++cc)
-    if (cc < NC) {
-      uint32_t r[32];
-      tmem_ld32(trow + cc * 32, r);
-      chunk_logits(a, ctx, cc, r, s[cc]);
-#pragma unroll
-      for (int t = 0; t < 32; ++t) mx = fmaxf(mx, s[cc][t]);
-    }
+    for (int t = 0; t < 32; ++t) mx = fmaxf(mx, s[t]);
+  }
   float sum = 0.f;
   const float mxl = mx * LOG2E;
+#pragma unroll 1
+  for (int cc = 0; cc < NC; ++cc) {                 // pass 2: exp, row sum, dropout, P -> shared memory
+    uint32_t r[32];
+    float s[32];
+    tmem_ld32(trow + cc * 32, r);
+    chunk_logits<VEC>(a, ctx, cc, r, s);
 #pragma unroll
-  for (int cc = 0; cc < 4; ++cc)
-    if (cc < NC) {
-#pragma unroll
-      for (int t = 0; t < 32; ++t) {
-        const float p = exp2f(fmaf(s[cc][t], LOG2E, -mxl));      // -inf -> 0
-        sum += p;
-        s[cc][t] = p;
-      }
-      if (use_drop && row_ok) {
-#pragma unroll
-        for (int g = 0; g < 8; ++g)
-          if (cc * 32 + 4 * g < Nk) {
-            float m[4];
-            drop4(a, ctx, key, cc * 32 + 4 * g, m);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) s[cc][4 * g + u] *= m[u];
-          }
-      }
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 pk = make_uint4(pack2(s[cc][8 * g], s[cc][8 * g + 1]), pack2(s[cc][8 * g + 2], s[cc][8 * g + 3]),
-                              pack2(s[cc][8 * g + 4], s[cc][8 * g + 5]), pack2(s[cc][8 * g + 6], s[cc][8 * g + 7]));
-        *reinterpret_cast<uint4*>(smem + 3 * TILE_BYTES + p_offset(i, cc * 4 + g)) = pk;
-      }
+    for (int t = 0; t < 32; ++t) {
+      s[t] = exp2f(fmaf(s[t], LOG2E, -mxl));        // -inf -> 0
+      sum += s[t];
     }
+    if (use_drop && row_ok) {
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        if (cc * 32 + 4 * g < Nk) {
+          float m[4];
+          drop4<VEC>(a, ctx, key, cc * 32 + 4 * g, m);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) s[4 * g + u] *= m[u];
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 pk = make_uint4(pack2(s[8 * g], s[8 * g + 1]), pack2(s[8 * g + 2], s[8 * g + 3]),
+                            pack2(s[8 * g + 4], s[8 * g + 5]), pack2(s[8 * g + 6], s[8 * g + 7]));
+      *reinterpret_cast<uint4*>(smem + p_offset(i, cc * 4 + g)) = pk;
+    }
+  }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy P writes -> visible to the MMA
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  __syncthreads();                                               // every thread has read its S columns: O may overwrite them
   if (tid == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t idesc = make_idesc(false, true, 128, 64);
     const int ksteps = (Nk + 15) >> 4;
     for (int t = 0; t < ksteps; ++t)
-      umma_bf16(tmem + 128, make_smem_desc(sP + (t >> 2) * TILE_BYTES + (t & 3) * 32, 16, 1024),
+      umma_bf16(tmem, make_smem_desc(sP + (t >> 2) * TILE_BYTES + (t & 3) * 32, 16, 1024),
                 make_smem_desc(sV + t * 2048, 8192, 1024), idesc, t > 0);
     umma_commit(bar + 16);
   }
   mbar_wait(bar + 16, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  pdl_launch();
   const float inv = sum > 0.f ? 1.f / sum : 0.f;
-#pragma unroll
+#pragma unroll 1
   for (int cc = 0; cc < 2; ++cc) {
     uint32_t r[32];
-    tmem_ld32(trow + 128 + cc * 32, r);
+    tmem_ld32(trow + cc * 32, r);
     if (row_ok) {
       __nv_bfloat16* orow = a.o + ((size_t)b * Nq + i) * a.ldo + h * 64 + cc * 32;
 #pragma unroll
@@ -236,9 +252,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
 }
 
+template <bool VEC>
 __global__ void __launch_bounds__(128, 2)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                    const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo, AttnTcArgs a) {
@@ -303,69 +320,69 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   const bool use_drop = a.drop.state != nullptr && a.drop.thresh > 0;
   const uint64_t key = use_drop ? drop_key(a.drop) : 0;
   const RowCtx ctx = make_row_ctx(a, b, h, i, row_ok, tid & 31);
-  float s[4][32];
   float mx = -INFINITY;
+#pragma unroll 1
+  for (int cc = 0; cc < NC; ++cc) {                 // pass 1: row maximum
+    uint32_t r[32];
+    float s[32];
+    tmem_ld32(trow + cc * 32, r);
+    chunk_logits<VEC>(a, ctx, cc, r, s);
 #pragma unroll
-  for (int cc = 0; cc < 4; ++cc)
-    if (cc < NC) {
-      uint32_t r[32];
-      tmem_ld32(trow + cc * 32, r);
-      chunk_logits(a, ctx, cc, r, s[cc]);
-#pragma unroll
-      for (int t = 0; t < 32; ++t) mx = fmaxf(mx, s[cc][t]);
-    }
+    for (int t = 0; t < 32; ++t) mx = fmaxf(mx, s[t]);
+  }
   float sum = 0.f;
   const float mxl = mx * LOG2E;
+#pragma unroll 1
+  for (int cc = 0; cc < NC; ++cc) {                 // pass 2: row sum
+    uint32_t r[32];
+    float s[32];
+    tmem_ld32(trow + cc * 32, r);
+    chunk_logits<VEC>(a, ctx, cc, r, s);
 #pragma unroll
-  for (int cc = 0; cc < 4; ++cc)
-    if (cc < NC) {
-#pragma unroll
-      for (int t = 0; t < 32; ++t) {
-        s[cc][t] = exp2f(fmaf(s[cc][t], LOG2E, -mxl));
-        sum += s[cc][t];
-      }
-    }
+    for (int t = 0; t < 32; ++t) sum += exp2f(fmaf(s[t], LOG2E, -mxl));
+  }
   const float inv = (row_ok && sum > 0.f) ? 1.f / sum : 0.f;     // rows >= Nq contribute zeros to dK / dV
   float* dbrow = (a.dbias && row_ok) ? a.dbias + ctx.rowbase : nullptr;
+#pragma unroll 1
+  for (int cc = 0; cc < NC; ++cc) {                 // pass 3: P (dropped), dS -> shared memory; d bias -> global
+    uint32_t r[32], rp[32];
+    float s[32], ds[32];
+    tmem_ld32(trow + cc * 32, r);
+    chunk_logits<VEC>(a, ctx, cc, r, s);
+    tmem_ld32(trow + 128 + cc * 32, rp);
+    const uint32_t mk = chunk_mask(ctx, cc);
 #pragma unroll
-  for (int cc = 0; cc < 4; ++cc)
-    if (cc < NC) {
-      uint32_t rp[32];
-      float ds[32];
-      tmem_ld32(trow + 128 + cc * 32, rp);
-      const uint32_t mk = ctx.mk[cc];
+    for (int g = 0; g < 8; ++g) {
+      float m[4] = {1.f, 1.f, 1.f, 1.f};
+      if (use_drop && cc * 32 + 4 * g < Nk) drop4<VEC>(a, ctx, key, cc * 32 + 4 * g, m);
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        float m[4] = {1.f, 1.f, 1.f, 1.f};
-        if (use_drop && cc * 32 + 4 * g < Nk) drop4(a, ctx, key, cc * 32 + 4 * g, m);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int t = 4 * g + u;
-          const float p = s[cc][t] * inv;                          // 0 for keys >= Nk (exp2(-inf)) and rows >= Nq
-          float d = p * (m[u] * __uint_as_float(rp[t]) - delta);
-          if (((mk >> t) & 1u) || p == 0.f) d = 0.f;               // masked_fill cuts the graph; p == 0 guards garbage dP
-          s[cc][t] = p * m[u];
-          ds[t] = d;
-        }
-        if (dbrow && cc * 32 + 4 * g < Nk) {
-          if (ctx.vec) {
-            *reinterpret_cast<float4*>(dbrow + cc * 32 + 4 * g) = make_float4(ds[4 * g], ds[4 * g + 1], ds[4 * g + 2], ds[4 * g + 3]);
-          } else {
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (cc * 32 + 4 * g + u < Nk) dbrow[cc * 32 + 4 * g + u] = ds[4 * g + u];
-          }
-        }
+      for (int u = 0; u < 4; ++u) {
+        const int t = 4 * g + u;
+        const float p = exp2f(fmaf(s[t], LOG2E, -mxl)) * inv;    // 0 for keys >= Nk (exp2(-inf)) and rows >= Nq
+        float d = p * (m[u] * __uint_as_float(rp[t]) - delta);
+        if (((mk >> t) & 1u) || p == 0.f) d = 0.f;               // masked_fill cuts the graph; p == 0 guards garbage dP
+        s[t] = p * m[u];
+        ds[t] = d;
       }
+      if (dbrow && cc * 32 + 4 * g < Nk) {
+        if (VEC) {
+          *reinterpret_cast<float4*>(dbrow + cc * 32 + 4 * g) = make_float4(ds[4 * g], ds[4 * g + 1], ds[4 * g + 2], ds[4 * g + 3]);
+        } else {
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const uint32_t off = p_offset(i, cc * 4 + g);
-        *reinterpret_cast<uint4*>(gP + off) = make_uint4(pack2(s[cc][8 * g], s[cc][8 * g + 1]), pack2(s[cc][8 * g + 2], s[cc][8 * g + 3]),
-                                                         pack2(s[cc][8 * g + 4], s[cc][8 * g + 5]), pack2(s[cc][8 * g + 6], s[cc][8 * g + 7]));
-        *reinterpret_cast<uint4*>(gdS + off) = make_uint4(pack2(ds[8 * g], ds[8 * g + 1]), pack2(ds[8 * g + 2], ds[8 * g + 3]),
-                                                          pack2(ds[8 * g + 4], ds[8 * g + 5]), pack2(ds[8 * g + 6], ds[8 * g + 7]));
+          for (int u = 0; u < 4; ++u)
+            if (cc * 32 + 4 * g + u < Nk) dbrow[cc * 32 + 4 * g + u] = ds[4 * g + u];
+        }
       }
     }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint32_t off = p_offset(i, cc * 4 + g);
+      *reinterpret_cast<uint4*>(gP + off) = make_uint4(pack2(s[8 * g], s[8 * g + 1]), pack2(s[8 * g + 2], s[8 * g + 3]),
+                                                       pack2(s[8 * g + 4], s[8 * g + 5]), pack2(s[8 * g + 6], s[8 * g + 7]));
+      *reinterpret_cast<uint4*>(gdS + off) = make_uint4(pack2(ds[8 * g], ds[8 * g + 1]), pack2(ds[8 * g + 2], ds[8 * g + 3]),
+                                                        pack2(ds[8 * g + 4], ds[8 * g + 5]), pack2(ds[8 * g + 6], ds[8 * g + 7]));
+    }
+  }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -396,7 +413,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     __nv_bfloat16* base = which == 0 ? a.dq + ((size_t)b * Nq + tid) * a.lddq
                         : which == 1 ? a.dk + ((size_t)b * Nk + tid) * a.lddk
                                      : a.dv + ((size_t)b * Nk + tid) * a.lddv;
-#pragma unroll
+#pragma unroll 1
     for (int cc = 0; cc < 2; ++cc) {
       uint32_t r[32];
       tmem_ld32(trow + which * 64 + cc * 32, r);
@@ -418,7 +435,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
 }
 
-constexpr int FWD_SMEM = 3 * TILE_BYTES + PTILE_BYTES + 1024 + 128;
+constexpr int FWD_SMEM = 3 * TILE_BYTES + 1024 + 128;
 constexpr int BWD_SMEM = 3 * TILE_BYTES + 2 * PTILE_BYTES + 128;
 
 DropCfg mk_drop(const unsigned long long* st, unsigned long long salt, float p) {
@@ -448,10 +465,12 @@ int mmnas_attn_fwd_tc(int B, int heads, int Nq, int Nk, const void* q, long ldq,
   a.o = (__nv_bfloat16*)o; a.ldo = ldo; a.scale = scale; a.drop = mk_drop(rng_state, salt, p);
   static bool attr_done = false;
   if (!attr_done) {
-    MMNAS_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    MMNAS_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    MMNAS_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
     attr_done = true;
   }
-  MMNAS_CUDA(mmnas_launch(attn_fwd_tc_kernel, dim3(heads, B), dim3(128), FWD_SMEM, s, tq, tk, tv, a));
+  if ((Nk & 3) == 0) MMNAS_CUDA(mmnas_launch(attn_fwd_tc_kernel<true>, dim3(heads, B), dim3(128), FWD_SMEM, s, tq, tk, tv, a));
+  else MMNAS_CUDA(mmnas_launch(attn_fwd_tc_kernel<false>, dim3(heads, B), dim3(128), FWD_SMEM, s, tq, tk, tv, a));
   return MMNAS_OK;
 }
 
@@ -476,9 +495,11 @@ int mmnas_attn_bwd_tc(int B, int heads, int Nq, int Nk, const void* q, long ldq,
   a.lddq = lddq; a.lddk = lddk; a.lddv = lddv; a.dbias = dbias;
   static bool attr_done = false;
   if (!attr_done) {
-    MMNAS_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    MMNAS_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    MMNAS_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
     attr_done = true;
   }
-  MMNAS_CUDA(mmnas_launch(attn_bwd_tc_kernel, dim3(heads, B), dim3(128), BWD_SMEM, s, tq, tk, tv, tdo, a));
+  if ((Nk & 3) == 0) MMNAS_CUDA(mmnas_launch(attn_bwd_tc_kernel<true>, dim3(heads, B), dim3(128), BWD_SMEM, s, tq, tk, tv, tdo, a));
+  else MMNAS_CUDA(mmnas_launch(attn_bwd_tc_kernel<false>, dim3(heads, B), dim3(128), BWD_SMEM, s, tq, tk, tv, tdo, a));
   return MMNAS_OK;
 }

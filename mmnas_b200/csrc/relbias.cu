@@ -11,7 +11,7 @@
 //  * every multiply-add is a packed FFMA2 (fma.rn.f32x2, two IEEE fp32 FMAs per issue slot);
 //  * the layer weights live in shared memory as ready-made pairs, staged by each CTA from the parameter tensors
 //    (no constant-bank staging copies, so the entry points are stream-safe);
-//  * forward: one thread per TWO pairs, FFMA2 packed over neighbouring rel channels (c, c+1);
+//  * forward: one thread per four pairs, FFMA2 packed over neighbouring rel channels (c, c+1);
 //  * backward: 128-pair tiles.  Phase A (thread = pair, packed over channels) recomputes e and r and parks e
 //    (transposed, padded) plus d pre_r / g (transposed) in shared memory.  Phase B (thread = channel c over half
 //    of the tile, packed over neighbouring PAIRS) forms d e = W_r[:,c] . d pre_r with its own weight column in
@@ -93,68 +93,87 @@ __device__ __forceinline__ u64 geo_channel_pair(const u64* Wy2, const u64* by2, 
   return pk2(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
 }
 
+// Forward: one thread per FPT pairs.  A broadcast LDS delivers 16 bytes to each of 32 lanes, i.e. costs four cycles of
+// the SM's 128 B/clk shared-memory return path, so the weight pairs are amortised over FPT pairs per thread; with
+// FPT = 4 the channel loop is bound by the FP32 pipe (24 FFMA2 issue slots per 7 weight loads were not).
+constexpr int FPT = 4;
+constexpr int FWD_THREADS = 128;
+
 template <int HEADS, bool DENSE>
-__global__ void __launch_bounds__(256) relbias_fwd_kernel(RelArgs a) {
+__global__ void __launch_bounds__(FWD_THREADS) relbias_fwd_kernel(RelArgs a) {
   extern __shared__ __align__(16) float sw[];
   pdl_wait(); pdl_launch();
-  stage_weights<HEADS, DENSE>(sw, a, threadIdx.x, 256);
+  stage_weights<HEADS, DENSE>(sw, a, threadIdx.x, FWD_THREADS);
   __syncthreads();
   const u64* Wy2 = reinterpret_cast<const u64*>(sw);
   const u64* by2 = Wy2 + R2 * 4;
   const u64* Wr2 = by2 + R2;
   const float* br = reinterpret_cast<const float*>(Wr2 + R2 * HEADS);
-  const unsigned p0 = 2u * (blockIdx.x * 256u + threadIdx.x), p1 = p0 + 1u;
+  const unsigned p0 = (unsigned)FPT * (blockIdx.x * (unsigned)FWD_THREADS + threadIdx.x);
   if (p0 >= a.pairs) return;
-  const bool two = p1 < a.pairs;
-  u64 rA[HEADS], rB[HEADS];
+  unsigned pr[FPT];                     // pairs past the end re-read pair p0 and are not stored
 #pragma unroll
-  for (int h = 0; h < HEADS; ++h) rA[h] = rB[h] = pk2(br[h], 0.f);
+  for (int q = 0; q < FPT; ++q) pr[q] = p0 + q < a.pairs ? p0 + q : p0;
+  u64 r[FPT][HEADS];
+#pragma unroll
+  for (int q = 0; q < FPT; ++q)
+#pragma unroll
+    for (int h = 0; h < HEADS; ++h) r[q][h] = pk2(br[h], 0.f);
   if (DENSE) {
-    const float4* eA = reinterpret_cast<const float4*>(a.rel + (size_t)p0 * R);
-    const float4* eB = reinterpret_cast<const float4*>(a.rel + (size_t)(two ? p1 : p0) * R);
-#pragma unroll 4
+#pragma unroll 2
     for (int c4 = 0; c4 < R / 4; ++c4) {
-      const float4 x = __ldg(eA + c4), y = __ldg(eB + c4);
-      const u64 xa = pk2(x.x, x.y), xb = pk2(x.z, x.w), ya = pk2(y.x, y.y), yb = pk2(y.z, y.w);
+      u64 ea[FPT], eb[FPT];
+#pragma unroll
+      for (int q = 0; q < FPT; ++q) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(a.rel + (size_t)pr[q] * R) + c4);
+        ea[q] = pk2(x.x, x.y); eb[q] = pk2(x.z, x.w);
+      }
 #pragma unroll
       for (int h = 0; h < HEADS; ++h) {
         const u64 w0 = Wr2[(2 * c4) * HEADS + h], w1 = Wr2[(2 * c4 + 1) * HEADS + h];
-        rA[h] = ffma2(w1, xb, ffma2(w0, xa, rA[h]));
-        rB[h] = ffma2(w1, yb, ffma2(w0, ya, rB[h]));
+#pragma unroll
+        for (int q = 0; q < FPT; ++q) r[q][h] = ffma2(w1, eb[q], ffma2(w0, ea[q], r[q][h]));
       }
     }
   } else {
-    const float4 ga = __ldg(reinterpret_cast<const float4*>(a.g4) + p0);
-    const float4 gb = __ldg(reinterpret_cast<const float4*>(a.g4) + (two ? p1 : p0));
-    const u64 gA[4] = {pk2(ga.x, ga.x), pk2(ga.y, ga.y), pk2(ga.z, ga.z), pk2(ga.w, ga.w)};
-    const u64 gB[4] = {pk2(gb.x, gb.x), pk2(gb.y, gb.y), pk2(gb.z, gb.z), pk2(gb.w, gb.w)};
-#pragma unroll 4
+    u64 gk[FPT][4];
+#pragma unroll
+    for (int q = 0; q < FPT; ++q) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(a.g4) + pr[q]);
+      gk[q][0] = pk2(g.x, g.x); gk[q][1] = pk2(g.y, g.y); gk[q][2] = pk2(g.z, g.z); gk[q][3] = pk2(g.w, g.w);
+    }
+#pragma unroll 2
     for (int c2 = 0; c2 < R2; ++c2) {
-      const u64 eA = geo_channel_pair<HEADS>(Wy2, by2, gA, c2);
-      const u64 eB = geo_channel_pair<HEADS>(Wy2, by2, gB, c2);
+      u64 e[FPT];
+#pragma unroll
+      for (int q = 0; q < FPT; ++q) e[q] = geo_channel_pair<HEADS>(Wy2, by2, gk[q], c2);
 #pragma unroll
       for (int h = 0; h < HEADS; ++h) {
         const u64 w = Wr2[c2 * HEADS + h];
-        rA[h] = ffma2(w, eA, rA[h]);
-        rB[h] = ffma2(w, eB, rB[h]);
+#pragma unroll
+        for (int q = 0; q < FPT; ++q) r[q][h] = ffma2(w, e[q], r[q][h]);
       }
     }
   }
   const unsigned b0 = p0 / a.nn, ij0 = p0 - b0 * a.nn;
-  float* o0 = a.bias + ((size_t)b0 * HEADS) * a.nn + ij0;
-  if (two && ij0 + 1u < a.nn && (a.nn & 1u) == 0u) {      // both pairs in one image, 8-byte aligned: one store per head
+  if (p0 + FPT <= a.pairs && ij0 + FPT <= a.nn && (a.nn & 3u) == 0u) {     // all in one image, 16-byte aligned
+    float* o = a.bias + ((size_t)b0 * HEADS) * a.nn + ij0;
 #pragma unroll
-    for (int h = 0; h < HEADS; ++h)
-      *reinterpret_cast<float2*>(o0 + (size_t)h * a.nn) =
-          make_float2(logf(fmaxf(fmaxf(sum2(rA[h]), 0.f), 1e-6f)), logf(fmaxf(fmaxf(sum2(rB[h]), 0.f), 1e-6f)));
+    for (int h = 0; h < HEADS; ++h) {
+      float v[FPT];
+#pragma unroll
+      for (int q = 0; q < FPT; ++q) v[q] = logf(fmaxf(fmaxf(sum2(r[q][h]), 0.f), 1e-6f));
+      *reinterpret_cast<float4*>(o + (size_t)h * a.nn) = make_float4(v[0], v[1], v[2], v[3]);
+    }
   } else {
 #pragma unroll
-    for (int h = 0; h < HEADS; ++h) o0[(size_t)h * a.nn] = logf(fmaxf(fmaxf(sum2(rA[h]), 0.f), 1e-6f));
-    if (two) {
-      const unsigned b1 = p1 / a.nn, ij1 = p1 - b1 * a.nn;
-      float* o1 = a.bias + ((size_t)b1 * HEADS) * a.nn + ij1;
+    for (int q = 0; q < FPT; ++q) {
+      const unsigned p = p0 + q;
+      if (p >= a.pairs) break;
+      const unsigned b = p / a.nn, ij = p - b * a.nn;
+      float* o = a.bias + ((size_t)b * HEADS) * a.nn + ij;
 #pragma unroll
-      for (int h = 0; h < HEADS; ++h) o1[(size_t)h * a.nn] = logf(fmaxf(fmaxf(sum2(rB[h]), 0.f), 1e-6f));
+      for (int h = 0; h < HEADS; ++h) o[(size_t)h * a.nn] = logf(fmaxf(fmaxf(sum2(r[q][h]), 0.f), 1e-6f));
     }
   }
 }
@@ -315,10 +334,11 @@ int check(int B, int N, int heads, int Rin, const float* rel, const float* g4, c
 
 template <int HEADS>
 int launch_fwd(const RelArgs& a, cudaStream_t s) {
-  const unsigned grid = (a.pairs + 511u) / 512u;             // two pairs per thread
+  constexpr unsigned per_cta = FPT * FWD_THREADS;
+  const unsigned grid = (a.pairs + per_cta - 1u) / per_cta;
   constexpr size_t smem = sizeof(float) * sw_floats<HEADS>();
-  if (a.rel) MMNAS_CUDA(mmnas_launch(relbias_fwd_kernel<HEADS, true>, dim3(grid), dim3(256), smem, s, a));
-  else MMNAS_CUDA(mmnas_launch(relbias_fwd_kernel<HEADS, false>, dim3(grid), dim3(256), smem, s, a));
+  if (a.rel) MMNAS_CUDA(mmnas_launch(relbias_fwd_kernel<HEADS, true>, dim3(grid), dim3(FWD_THREADS), smem, s, a));
+  else MMNAS_CUDA(mmnas_launch(relbias_fwd_kernel<HEADS, false>, dim3(grid), dim3(FWD_THREADS), smem, s, a));
   return MMNAS_OK;
 }
 
