@@ -320,31 +320,31 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   const bool use_drop = a.drop.state != nullptr && a.drop.thresh > 0;
   const uint64_t key = use_drop ? drop_key(a.drop) : 0;
   const RowCtx ctx = make_row_ctx(a, b, h, i, row_ok, tid & 31);
-  float mx = -INFINITY;
+  float mx = -INFINITY, sum = 0.f;
 #pragma unroll 1
-  for (int cc = 0; cc < NC; ++cc) {                 // pass 1: row maximum
+  for (int cc = 0; cc < NC; ++cc) {                 // pass 1: row maximum and row sum together (running rescale)
     uint32_t r[32];
     float s[32];
     tmem_ld32(trow + cc * 32, r);
     chunk_logits<VEC>(a, ctx, cc, r, s);
+    float cm = s[0];
 #pragma unroll
-    for (int t = 0; t < 32; ++t) mx = fmaxf(mx, s[t]);
+    for (int t = 1; t < 32; ++t) cm = fmaxf(cm, s[t]);
+    const float nm = fmaxf(mx, cm);                 // finite from chunk 0 on: key 0 is never -inf
+    const float nml = nm * LOG2E;
+    float part = 0.f;
+#pragma unroll
+    for (int t = 0; t < 32; ++t) part += exp2f(fmaf(s[t], LOG2E, -nml));
+    // rescale by exactly the ratio of the two term scalings (1 when the maximum did not move, even at -1e9 where
+    // the rounded products carry errors of +-64; 0 on the first chunk, mx = -inf)
+    sum = fmaf(sum, exp2f(__fmul_rn(mx, LOG2E) - nml), part);      // __fmul_rn: no contraction into an fma
+    mx = nm;
   }
-  float sum = 0.f;
   const float mxl = mx * LOG2E;
-#pragma unroll 1
-  for (int cc = 0; cc < NC; ++cc) {                 // pass 2: row sum
-    uint32_t r[32];
-    float s[32];
-    tmem_ld32(trow + cc * 32, r);
-    chunk_logits<VEC>(a, ctx, cc, r, s);
-#pragma unroll
-    for (int t = 0; t < 32; ++t) sum += exp2f(fmaf(s[t], LOG2E, -mxl));
-  }
   const float inv = (row_ok && sum > 0.f) ? 1.f / sum : 0.f;     // rows >= Nq contribute zeros to dK / dV
   float* dbrow = (a.dbias && row_ok) ? a.dbias + ctx.rowbase : nullptr;
 #pragma unroll 1
-  for (int cc = 0; cc < NC; ++cc) {                 // pass 3: P (dropped), dS -> shared memory; d bias -> global
+  for (int cc = 0; cc < NC; ++cc) {                 // pass 2: P (dropped), dS -> shared memory; d bias -> global
     uint32_t r[32], rp[32];
     float s[32], ds[32];
     tmem_ld32(trow + cc * 32, r);
