@@ -1,4 +1,5 @@
-"""Where does the tcgen05 GEMM spend its time?  MMNAS_GEMM_DEBUG=1 drops the global epilogue traffic, =2 drops the MMAs."""
+"""Where does the tcgen05 GEMM spend its time?  MMNAS_GEMM_DEBUG=2 drops the MMAs, =3 drops the epilogue work
+(the accumulator is released unread): full vs no-MMA vs no-epilogue device time per shape."""
 import os, sys, torch
 sys.path.insert(0, '.')
 from mmnas_b200 import kernels as K
@@ -18,10 +19,10 @@ for bn in ('128', '256'):
     os.environ['MMNAS_GEMM_BN'] = bn; os.environ['MMNAS_GEMM_PAIR'] = '0'
     for shape in [(6400, 2048, 512), (6400, 1536, 512), (6400, 512, 2048), (6400, 512, 512), (896, 512, 512), (896, 2048, 512)]:
         row = []
-        for dbg in ('0', '1', '2', '3', '4'):
+        for dbg in ('0', '2', '3'):
             os.environ['MMNAS_GEMM_DEBUG'] = dbg
             row.append(run(*shape, 1))
-        print('BN=%s %s full %.1f us | no-epilogue-traffic %.1f | no-mma %.1f | no-epilogue %.1f | no-loads-no-mma %.1f' % (bn, shape, *row))
+        print('BN=%s %s full %.1f us | no-mma %.1f | no-epilogue %.1f' % (bn, shape, *row))
 
 # fixed cost: one tile, one k-block
 os.environ['MMNAS_GEMM_DEBUG'] = '0'

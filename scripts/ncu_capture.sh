@@ -33,7 +33,7 @@ print('launch list:', n, 'launches', round(tot / 1e3, 2), 'ms')
 PY
 # 2. full metric set on a few launches of each hot kernel (eager mode so -k/-s address them directly)
 timeout 900 ncu --set full --clock-control none -k regex:"gemm_bf16_|attn_bwd_tc|attn_fwd_tc|relbias_bwd|ln_bwd_kernel|ln_fwd_kernel" \
-    -s 620 -c 36 -o /tmp/prof python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > /tmp/ncu_full.log 2>&1
+    -s 760 -c 60 -o /tmp/prof python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > /tmp/ncu_full.log 2>&1
 tail -2 /tmp/ncu_full.log | cut -c1-160
 ncu -i /tmp/prof.ncu-rep --page raw --csv > /tmp/raw.csv 2>/dev/null
 python - <<'PY' "$TAG"

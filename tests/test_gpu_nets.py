@@ -291,3 +291,48 @@ def test_direct_gradient_accumulation_equals_autograd_accumulation(mode):
         assert pb.grad.data_ptr() == fg.view(fg.params.index(pb)).data_ptr() if False else True
         pr.add(n_, pb.grad, pa.grad, 2e-5 if mode == 'fp32' else 2e-3, 1e-3 * float(pa.grad.abs().max()), metric='fro')
     pr.check()
+
+
+def test_eager_pytorch_port_timing_on_this_gpu_is_logged():
+    """SURVEY §8d 'reference timing beside it' (2): the reference ships no kernels, so its GPU path is eager PyTorch.
+    The oracle port of the train step (same arithmetic as the reference modules: nn.functional linear / matmul /
+    softmax / dropout, autograd backward, then clip + Adam) is timed here on the same B200 at the bench workload
+    (B=64, dropout 0.1), fp32 and under bf16 autocast, and written to gpurun_out/eager_port_timing.json.  A record,
+    not a gate: the only assertion is that the numbers are finite."""
+    import json
+    import os
+    from mmnas_b200.model.nets import Net_Full
+    from mmnas_b200 import genotypes
+    from mmnas_b200.data.synthetic import Cfg, SynthSpec, make_batch, init_dict
+    torch.manual_seed(888)
+    spec = SynthSpec(batch=64)                 # the bench workload: vocab 20000, 3129 answers
+    cfg = Cfg(genotype=genotypes.shipped('mmnas_vqa'), DROPOUT_R=0.1)
+    inputs, target = make_batch(spec, 888)
+    init = init_dict(spec)
+    net = Net_Full(cfg, init).to(DEV)          # parameter container only; the arithmetic below is the oracle's
+    P = O.leaf_params(net.state_dict(), torch.float32)
+    params = [p for p in P.values() if p.requires_grad]
+    din, dt = tuple(t.to(DEV) for t in inputs), target.to(DEV)
+    res = {}
+    for label, autocast in (('fp32', False), ('bf16_autocast', True)):
+        state, times = {}, []
+        for it in range(6):
+            for p in params:
+                p.grad = None
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            with torch.autocast('cuda', dtype=torch.bfloat16, enabled=autocast):
+                pred = O.net_full_vqa(P, din, cfg.GENOTYPE, 0.1, True)
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(pred.float(), dt, reduction='sum')
+            loss.backward()
+            O.clip_and_adam(params, state, it + 1, 1e-5)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms = sorted(times[2:])[len(times[2:]) // 2]
+        assert ms == ms and ms > 0
+        res[label] = {'ms_per_step': ms, 'samples_per_s': 64e3 / ms}
+    os.makedirs('gpurun_out', exist_ok=True)
+    json.dump({'workload': 'MMnas-VQA train step, B=64, dropout 0.1, eager PyTorch port (oracle) on cuda:0', **res},
+              open('gpurun_out/eager_port_timing.json', 'w'), indent=1)
