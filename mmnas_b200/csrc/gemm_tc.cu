@@ -65,6 +65,11 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32
   asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
+// hint: bring a tile into L2 (no shared-memory destination, no barrier); legal before griddepcontrol.wait because L2
+// is the coherence point — a line the predecessor rewrites afterwards is simply updated in place
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
@@ -234,6 +239,20 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   if (warp == 0 && lane == 0) {
     // ===== TMA producer =====
+    if (blockIdx.x < units) {                     // warm L2 with the first stages of B (weights: cold, a step old)
+      int z, m0, n0, kb0, nkb;
+      decode(blockIdx.x, z, m0, n0, kb0, nkb);
+      const int pre = nkb < STAGES ? nkb : STAGES;
+      for (int i = 0; i < pre; ++i) {
+        const int k0 = (kb0 + i) * BK;
+        if (!B_MN) {
+          tma_prefetch_2d(&tmap_b, k0, n0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c) tma_prefetch_2d(&tmap_b, n0 + 64 * c, k0);
+        }
+      }
+    }
     pdl_wait();                                   // operands come from the previous kernel(s) of the stream
     uint32_t it = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
@@ -309,7 +328,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       if (lane == 0) mbar_arrive(tempty_bar(buf));
     }
-    if (lane == 0) bulk_wait<0>();                // every store / reduce of this warp has been performed
+    if (lane == 0) bulk_wait_read<0>();           // the TMA unit has read the last boxes: shared memory may be released
+                                                  // (the writes themselves complete before the grid does)
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -467,7 +487,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       if (lane == 0) mbar_arrive_cluster(buf ? te1 : te0);
     }
-    if (lane == 0) bulk_wait<0>();
+    if (lane == 0) bulk_wait_read<0>();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();

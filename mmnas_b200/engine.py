@@ -13,6 +13,8 @@ Pieces
   TrainStep / SearchStep   the step bodies; TrainStep can replay the whole step as one CUDA graph.
   Prefetcher     pinned host batches -> device on a copy stream, double buffered.
 """
+import os
+
 import torch
 import torch.distributed as dist
 import torch.nn.functional as F
@@ -60,6 +62,7 @@ class BucketReducer:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.enabled = self.world > 1
         self.buckets = []          # (start, end, [param indices]) over the flat buffer, reverse registration order
+        bucket_mb = float(os.environ.get('MMNAS_BUCKET_MB', bucket_mb))      # tuning / A-B experiments only
         cap = int(bucket_mb * (1 << 20) / 4)
         idxs, end = [], None
         n = len(self.fg.params)
