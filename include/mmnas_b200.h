@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MMNAS_B200_ABI_VERSION 5
+#define MMNAS_B200_ABI_VERSION 6
 
 typedef void* mmnas_stream;
 
@@ -65,11 +65,14 @@ int mmnas_attn_bwd(int dtype, int B, int heads, int Nq, int Nk, int head_dim, co
 
 /* ---- RSA geometry bias: log(clamp(relu(linear_r(rel_embed)), 1e-6)) (modules.py:231,235) --------------
  * Exactly one of rel [B,N,N,R] (the reference's dense tensor) or g4 [B,N,N,4] (+Wy [R,4], by [R]: the
- * relu(linear_y_rel(.)) of full_vqa.py:103 folded in) is non-NULL.  bias out: [B,heads,N,N].  R == 64, heads <= 16. */
-int mmnas_relbias_fwd(int B, int N, int heads, int R, const float* rel, const float* g4, const float* Wy,
+ * relu(linear_y_rel(.)) of full_vqa.py:103 folded in) is non-NULL.  bias out: [B,heads,N,N].  R == 64, heads <= 16.
+ * mode 0: fp32 arithmetic (parity arm).  mode 1 (bf16 arm): the 64-channel contractions run on the tensor cores with
+ * split-bf16 operands for r and plain bf16 operands for the gradient products (geometry input, 8 heads; any other
+ * configuration silently uses the mode-0 kernels). */
+int mmnas_relbias_fwd(int mode, int B, int N, int heads, int R, const float* rel, const float* g4, const float* Wy,
                       const float* by, const float* Wr, const float* br, float* bias, mmnas_stream stream);
 /* Backward: dWr/dbr (and dWy/dby, geometry mode) are ACCUMULATED (caller zeroes); drel [B,N,N,R] written (dense mode). */
-int mmnas_relbias_bwd(int B, int N, int heads, int R, const float* rel, const float* g4, const float* Wy,
+int mmnas_relbias_bwd(int mode, int B, int N, int heads, int R, const float* rel, const float* g4, const float* Wy,
                       const float* by, const float* Wr, const float* br, const float* dbias, float* drel, float* dWy,
                       float* dby, float* dWr, float* dbr, mmnas_stream stream);
 

@@ -10,7 +10,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libmmnas_b200.so')
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 c_p, c_i, c_l, c_f, c_u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float, ctypes.c_ulonglong
 
@@ -24,8 +24,8 @@ SIGNATURES = {
                        c_f, c_p],
     'mmnas_attn_bwd': [c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_l, c_p, c_l, c_p, c_l, c_p, c_p, c_p, c_l, c_p, c_l, c_p,
                        c_l, c_p, c_l, c_p, c_l, c_p, c_f, c_p, c_u64, c_f, c_p],
-    'mmnas_relbias_fwd': [c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
-    'mmnas_relbias_bwd': [c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
+    'mmnas_relbias_fwd': [c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
+    'mmnas_relbias_bwd': [c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     'mmnas_ln_residual_fwd': [c_i, c_i, c_p, c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_p, c_p, c_u64, c_f, c_p],
     'mmnas_ln_residual_bwd': [c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_f, c_p, c_p, c_i, c_p, c_p, c_p, c_u64, c_f, c_p],
     'mmnas_mixed_accum': [c_i, c_p, c_p, c_p, c_l, c_p],

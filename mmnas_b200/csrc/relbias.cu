@@ -369,30 +369,46 @@ int launch_bwd(const RelArgs& a, cudaStream_t s) {
 
 }  // namespace
 
-extern "C" int mmnas_relbias_fwd(int B, int N, int heads, int Rin, const float* rel, const float* g4, const float* Wy,
-                                 const float* by, const float* Wr, const float* br, float* bias,
+int mmnas_relbias_fwd_mma(int B, int N, int heads, const float* g4, const float* Wy, const float* by, const float* Wr,
+                          const float* br, float* bias, cudaStream_t s);
+int mmnas_relbias_bwd_mma(int B, int N, int heads, const float* g4, const float* Wy, const float* by, const float* Wr,
+                          const float* br, const float* dbias, float* dWy, float* dby, float* dWr, float* dbr,
+                          cudaStream_t s);
+
+extern "C" int mmnas_relbias_fwd(int mode, int B, int N, int heads, int Rin, const float* rel, const float* g4,
+                                 const float* Wy, const float* by, const float* Wr, const float* br, float* bias,
                                  mmnas_stream stream) {
   int rc = check(B, N, heads, Rin, rel, g4, Wy, by, Wr, br);
   if (rc) return rc;
+  MMNAS_CHECK_ARG(mode == 0 || mode == 1, "relbias_fwd: mode must be 0 (fp32 arithmetic) or 1 (tensor-core arithmetic)");
   if (B == 0) return MMNAS_OK;
   MMNAS_CHECK_ARG(bias, "relbias_fwd: null output");
   cudaStream_t s = (cudaStream_t)stream;
+  if (mode == 1 && g4) {
+    rc = mmnas_relbias_fwd_mma(B, N, heads, g4, Wy, by, Wr, br, bias, s);
+    if (rc != MMNAS_ERR_UNSUPPORTED) return rc;
+  }
   RelArgs a = {};
   a.B = B; a.N = N; a.heads = heads; a.nn = (unsigned)N * N; a.pairs = (unsigned)B * a.nn;
   a.rel = rel; a.g4 = g4; a.Wy = Wy; a.by = by; a.Wr = Wr; a.br = br; a.bias = bias;
   DISPATCH_HEADS(launch_fwd, heads, a, s)
 }
 
-extern "C" int mmnas_relbias_bwd(int B, int N, int heads, int Rin, const float* rel, const float* g4, const float* Wy,
-                                 const float* by, const float* Wr, const float* br, const float* dbias, float* drel,
-                                 float* dWy, float* dby, float* dWr, float* dbr, mmnas_stream stream) {
+extern "C" int mmnas_relbias_bwd(int mode, int B, int N, int heads, int Rin, const float* rel, const float* g4,
+                                 const float* Wy, const float* by, const float* Wr, const float* br, const float* dbias,
+                                 float* drel, float* dWy, float* dby, float* dWr, float* dbr, mmnas_stream stream) {
   int rc = check(B, N, heads, Rin, rel, g4, Wy, by, Wr, br);
   if (rc) return rc;
+  MMNAS_CHECK_ARG(mode == 0 || mode == 1, "relbias_bwd: mode must be 0 (fp32 arithmetic) or 1 (tensor-core arithmetic)");
   if (B == 0) return MMNAS_OK;
   MMNAS_CHECK_ARG(dbias && dWr && dbr, "relbias_bwd: null buffer");
   MMNAS_CHECK_ARG(!rel || drel, "relbias_bwd: dense mode needs d rel_embed output");
   MMNAS_CHECK_ARG(!g4 || (dWy && dby), "relbias_bwd: geometry mode needs dWy/dby outputs");
   cudaStream_t s = (cudaStream_t)stream;
+  if (mode == 1 && g4) {
+    rc = mmnas_relbias_bwd_mma(B, N, heads, g4, Wy, by, Wr, br, dbias, dWy, dby, dWr, dbr, s);
+    if (rc != MMNAS_ERR_UNSUPPORTED) return rc;
+  }
   RelArgs a = {};
   a.B = B; a.N = N; a.heads = heads; a.nn = (unsigned)N * N; a.pairs = (unsigned)B * a.nn;
   a.rel = rel; a.g4 = g4; a.Wy = Wy; a.by = by; a.Wr = Wr; a.br = br; a.dbias = dbias; a.drel = drel; a.dWy = dWy; a.dby = dby; a.dWr = dWr; a.dbr = dbr;

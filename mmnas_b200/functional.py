@@ -194,14 +194,14 @@ class AttBlockFn(Function):
                 K.gemm_f32(Mq, I, H, x, H, 1, Wq, 1, H, q, I)
                 K.gemm_f32(Mk, I, H, kvt, H, 1, Wk, 1, H, k, 2 * I)
                 K.gemm_f32(Mk, I, H, kvt, H, 1, Wv, 1, H, v, 2 * I)
-        # --- RSA logit bias from the geometry path (fp32 in both arms)
+        # --- RSA logit bias from the geometry path (fp32 kernels; tensor-core arithmetic with split operands in the bf16 arm)
         bias = None
         R = 0
         if Wr is not None:
             R = Wr.shape[1]
             bias = _empty((B, heads, Nq, Nk), torch.float32, dev)
             if g4 is not None:
-                K.relbias_fwd(B, Nq, heads, R, None, g4.contiguous(), Wy, by, Wr, br, bias)
+                K.relbias_fwd(B, Nq, heads, R, None, g4.contiguous(), Wy, by, Wr, br, bias, mode=1 if bf else 0)
             else:
                 rel = rel.contiguous()
                 K.relbias_fwd(B, Nq, heads, R, rel, None, None, None, Wr, br, bias)
@@ -303,7 +303,8 @@ class AttBlockFn(Function):
             s_Wr, s_br = _Sink([Wr], dev).prepare(True), _Sink([br], dev).prepare(True)
             if g4 is not None:
                 s_Wy, s_by = _Sink([Wy], dev).prepare(True), _Sink([by], dev).prepare(True)
-                K.relbias_bwd(B, Nq, heads, R, None, g4, Wy, by, Wr, br, dbias, None, s_Wy.buf, s_by.buf, s_Wr.buf, s_br.buf)
+                K.relbias_bwd(B, Nq, heads, R, None, g4, Wy, by, Wr, br, dbias, None, s_Wy.buf, s_by.buf, s_Wr.buf, s_br.buf,
+                              mode=1 if bf else 0)
                 g_Wy, g_by = s_Wy.grads()[0], s_by.grads()[0]
             else:
                 drel = torch.empty_like(rel)

@@ -64,12 +64,13 @@ def attn_bwd(B, heads, Nq, Nk, q, ldq, k, ldk, v, ldv, kmask, bias, o, ldo, dout
          ptr(o), ldo, ptr(dout), lddo, dq, lddq, dk, lddk, dv, lddv, ptr(dbias), scale, st, salt, p, stream())
 
 
-def relbias_fwd(B, N, heads, R, rel, g4, Wy, by, Wr, br, bias):
-    call('mmnas_relbias_fwd', B, N, heads, R, ptr(rel), ptr(g4), ptr(Wy), ptr(by), ptr(Wr), ptr(br), ptr(bias), stream())
+def relbias_fwd(B, N, heads, R, rel, g4, Wy, by, Wr, br, bias, mode=0):
+    """mode 0 = fp32 arithmetic, 1 = tensor-core arithmetic (bf16 arm)"""
+    call('mmnas_relbias_fwd', mode, B, N, heads, R, ptr(rel), ptr(g4), ptr(Wy), ptr(by), ptr(Wr), ptr(br), ptr(bias), stream())
 
 
-def relbias_bwd(B, N, heads, R, rel, g4, Wy, by, Wr, br, dbias, drel, dWy, dby, dWr, dbr):
-    call('mmnas_relbias_bwd', B, N, heads, R, ptr(rel), ptr(g4), ptr(Wy), ptr(by), ptr(Wr), ptr(br), ptr(dbias),
+def relbias_bwd(B, N, heads, R, rel, g4, Wy, by, Wr, br, dbias, drel, dWy, dby, dWr, dbr, mode=0):
+    call('mmnas_relbias_bwd', mode, B, N, heads, R, ptr(rel), ptr(g4), ptr(Wy), ptr(by), ptr(Wr), ptr(br), ptr(dbias),
          ptr(drel), ptr(dWy), ptr(dby), ptr(dWr), ptr(dbr), stream())
 
 

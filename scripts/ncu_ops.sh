@@ -27,9 +27,9 @@ for _ in range(3):
 torch.cuda.synchronize()
 PY
 for K in ${KERNELS:-relbias_fwd relbias_bwd attn_fwd_tc attn_bwd_tc}; do
-  timeout 300 ncu --set full --import-source on --clock-control none -k regex:"$K" -s 2 -c 1 -o /tmp/op_$K -f python /tmp/one_rsa.py > /tmp/ncu_$K.log 2>&1
+  timeout 300 ncu --set full --import-source on --clock-control none -k regex:"$K" -s ${SKIP:-2} -c 1 -o /tmp/op_$K -f python /tmp/one_rsa.py > /tmp/ncu_$K.log 2>&1
   tail -1 /tmp/ncu_$K.log | cut -c1-150
-  ncu -i /tmp/op_$K.ncu-rep --page source --csv --print-source sass > gpurun_out/src_$K.csv 2>/dev/null
-  ncu -i /tmp/op_$K.ncu-rep --page details --csv > gpurun_out/det_$K.csv 2>/dev/null
+  ncu -i /tmp/op_$K.ncu-rep --page source --csv --print-source sass > gpurun_out/src_$K${SUFFIX:-}.csv 2>/dev/null
+  ncu -i /tmp/op_$K.ncu-rep --page details --csv > gpurun_out/det_$K${SUFFIX:-}.csv 2>/dev/null
 done
 ls -la gpurun_out/src_* gpurun_out/det_* | cut -c20-200

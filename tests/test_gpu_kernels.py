@@ -424,3 +424,39 @@ def test_sumsq_is_bit_reproducible_and_exact_enough():
     assert float(out) == 0.0
     k.sumsq(x[:8], out, scratch)                                      # one block
     assert abs(float(out) - float((x[:8].double() ** 2).sum())) < 1e-6
+
+
+@pytest.mark.parametrize('B,N', [(3, 100), (1, 37), (2, 5), (64, 100)])
+def test_relbias_tensor_core_mode_matches_fp64(B, N):
+    """mode 1 of mmnas_relbias_fwd / _bwd (bf16 arm: warp-level mma.sync on register fragments, split-bf16 operands
+    for r, plain bf16 operands for the gradient products) against the float64 formula and against the mode-0 kernels,
+    8 heads, geometry input; pair counts that are not multiples of 32 / 16 exercise the dead-row handling."""
+    k = K()
+    R, h = 64, 8
+    g4 = rnd(B, N, N, 4, seed=1)
+    g4[0, N // 2:] = 0                    # zero-padded pairs, as the loader produces
+    Wy, by = 0.5 * rnd(R, 4, seed=2), 0.1 * rnd(R, seed=3)
+    Wr, br = 0.03 * rnd(h, R, seed=4), torch.ones(h, device=DEV)       # benign regime (see test_relbias_fwd_bwd)
+    br[0] = -2.0
+    go = rnd(B, h, N, N, seed=6)
+    g4d, Wyd, byd, Wrd, brd = (t.double().requires_grad_(True) for t in (g4, Wy, by, Wr, br))
+    e = torch.relu(g4d @ Wyd.t() + byd)
+    r = torch.relu(e @ Wrd.t() + brd).permute(0, 3, 1, 2)
+    ref = torch.log(torch.clamp(r, min=1e-6))
+    ref.backward(go.double())
+    bias = torch.empty(B, h, N, N, device=DEV)
+    k.relbias_fwd(B, N, h, R, None, g4, Wy, by, Wr, br, bias, mode=1)
+    safe = (r.detach() > 1e-4) | (r.detach() == 0)
+    # split operands: r carries an absolute error ~1e-5 of its largest term, which the logarithm turns into a relative
+    # one; at r = 1e-4 (the edge of `safe`) that is a few per cent of one logit unit, 4.5e-5 of the -13.8 range
+    assert normwise(bias[safe], ref[safe]) < 2e-4
+    dWr, dbr, dWy, dby = torch.zeros_like(Wr), torch.zeros_like(br), torch.zeros_like(Wy), torch.zeros_like(by)
+    k.relbias_bwd(B, N, h, R, None, g4, Wy, by, Wr, br, go, None, dWy, dby, dWr, dbr, mode=1)
+    tol = 1e-2                                             # bf16 operands in the gradient products
+    assert normwise(dWr, Wrd.grad) < tol
+    assert normwise(dbr, brd.grad) < tol
+    assert normwise(dWy, Wyd.grad) < tol
+    assert normwise(dby, byd.grad) < tol
+    bias0 = torch.empty_like(bias)
+    k.relbias_fwd(B, N, h, R, None, g4, Wy, by, Wr, br, bias0, mode=0)
+    assert normwise(bias[safe], bias0[safe]) < 2e-4
