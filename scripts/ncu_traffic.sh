@@ -12,7 +12,7 @@ rows = [r for r in csv.reader(open('/tmp/traffic.csv')) if len(r) > 5]
 hdr = next(i for i, r in enumerate(rows) if 'Kernel Name' in r)
 H = rows[hdr]
 ki, mi, vi, ui, idi = H.index('Kernel Name'), H.index('Metric Name'), H.index('Metric Value'), H.index('Metric Unit'), H.index('ID')
-fam_of = [('gemm_bf16_', 'gemm_bf16_tc'), ('attn_bwd', 'attn_bwd'), ('attn_fwd', 'attn_fwd'), ('relbias_bwd', 'relbias_bwd'),
+fam_of = [('gemm_bf16_', 'gemm_bf16_tc'), ('attn_bwd', 'attn_bwd'), ('attn_fwd', 'attn_fwd'), ('relbias_mma', 'relbias_mma'), ('relbias_bwd', 'relbias_bwd'),
           ('relbias_fwd', 'relbias_fwd'), ('ln_bwd', 'ln_residual_bwd'), ('ln_fwd', 'ln_residual_fwd'), ('colsum', 'colsum'),
           ('cast_multi', 'cast_multi'), ('cast_kernel', 'cast_f32_to_bf16'), ('mixed_', 'mixed')]
 scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 'nsecond': 1e-3, 'usecond': 1.0, 'msecond': 1e3, '%': 1.0}
