@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(THREADS, BWD ? 1 : 2) relbias_mma_kernel(MmaAr
         mma16816(rr[mt], e_hi[mt][0][2 * k], e_hi[mt][1][2 * k], e_hi[mt][0][2 * k + 1], e_hi[mt][1][2 * k + 1], wr_lo[k][0], wr_lo[k][1]);
       }
     }
-    if (!BWD) {
+    if constexpr (!BWD) {
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -181,8 +181,7 @@ __global__ void __launch_bounds__(THREADS, BWD ? 1 : 2) relbias_mma_kernel(MmaAr
             o[0] = logf(fmaxf(fmaxf(rr[mt][2 * rh], 0.f), 1e-6f));
             o[a.nn] = logf(fmaxf(fmaxf(rr[mt][2 * rh + 1], 0.f), 1e-6f));
           }
-      continue;
-    }
+    } else {
     // ---- backward
     uint32_t dp[2][2];                   // d pre_r as A-fragment rows (K = heads 2q, 2q+1)
 #pragma unroll
@@ -230,6 +229,7 @@ __global__ void __launch_bounds__(THREADS, BWD ? 1 : 2) relbias_mma_kernel(MmaAr
         mma16816(accWy[m], tile_t(de[0][2 * m]), tile_t(de[0][2 * m + 1]), tile_t(de[1][2 * m]), tile_t(de[1][2 * m + 1]), gq0, gq1);
       }
     }
+    }   // backward
   }
   if (!BWD) return;
   // ---- CTA reduction, then one global atomic per output.  Accumulator (m, i): channel 16m + g + 8 (i >> 1), column 2q + (i & 1)

@@ -460,3 +460,72 @@ def test_relbias_tensor_core_mode_matches_fp64(B, N):
     bias0 = torch.empty_like(bias)
     k.relbias_fwd(B, N, h, R, None, g4, Wy, by, Wr, br, bias0, mode=0)
     assert normwise(bias[safe], bias0[safe]) < 2e-4
+
+
+def test_gemm_bf16_random_sweep():
+    """Seeded sweep over sizes, operand layouts, tilings (single CTA 128 / 256 wide, CTA pair), split-K, output types,
+    pitched outputs and epilogues of mmnas_gemm_bf16 against float64: ragged M, K not a multiple of 64 (TMA zero fill),
+    N = 32 .. 2048, one-row problems."""
+    import os
+    import random
+    k = K()
+    rng = random.Random(1234)
+    prev = {v: os.environ.get(v) for v in ('MMNAS_GEMM_PAIR', 'MMNAS_GEMM_BN')}
+    try:
+        for case in range(60):
+            M = rng.choice([1, 7, 64, 127, 128, 129, 300, 896, 1000, 2049])
+            N = rng.choice([32, 64, 96, 128, 256, 320, 512, 768, 2048])
+            Kd = rng.choice([8, 16, 40, 64, 72, 200, 512, 1000])
+            a_mn, b_mn = rng.randint(0, 1), rng.randint(0, 1)
+            mode = rng.choice(['bf16', 'f32', 'f32_acc', 'splitk', 'bias_relu', 'aux', 'pitched'])
+            for var, val in (('MMNAS_GEMM_PAIR', rng.choice([None, '0', '1'])), ('MMNAS_GEMM_BN', rng.choice([None, '128', '256']))):
+                if val is None:
+                    os.environ.pop(var, None)
+                else:
+                    os.environ[var] = val
+            Kp, Mp = (Kd + 7) // 8 * 8, (M + 7) // 8 * 8
+            A = rnd(Kp if a_mn else M, Mp if a_mn else Kp, seed=3 * case + 1, dtype=torch.bfloat16)
+            B = rnd(Kp if b_mn else N, N if b_mn else Kp, seed=3 * case + 2, dtype=torch.bfloat16)
+            Ad = (A[:Kd, :M].t() if a_mn else A[:, :Kd]).double()
+            Bd = (B[:Kd] if b_mn else B[:, :Kd].t()).double()
+            ref = Ad @ Bd
+            tag = (case, M, N, Kd, a_mn, b_mn, mode, os.environ.get('MMNAS_GEMM_PAIR'), os.environ.get('MMNAS_GEMM_BN'))
+            args = (M, N, Kd, A, A.stride(0), a_mn, B, B.stride(0), b_mn)
+            if mode == 'bf16':
+                C = torch.full((M, N), float('nan'), device=DEV, dtype=torch.bfloat16)
+                k.gemm_bf16(*args, C, N)
+                assert normwise(C, ref) < 6e-3, tag
+            elif mode == 'f32':
+                C = torch.full((M, N), float('nan'), device=DEV)
+                k.gemm_bf16(*args, C, N)
+                assert normwise(C, ref) < 1e-5, tag
+            elif mode == 'f32_acc':
+                C = rnd(M, N, seed=3 * case + 3)
+                want = C.double() + ref
+                k.gemm_bf16(*args, C, N, accumulate=True)
+                assert normwise(C, want) < 1e-5, tag
+            elif mode == 'splitk':
+                C = torch.zeros(M, N, device=DEV)
+                k.gemm_bf16(*args, C, N, split_k=rng.choice([2, 3, 5]))
+                assert normwise(C, ref) < 1e-5, tag
+            elif mode == 'bias_relu':
+                bias = rnd(N, seed=3 * case + 3)
+                C = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+                k.gemm_bf16(*args, C, N, bias=bias, relu=True)
+                assert normwise(C, torch.relu(ref + bias.double())) < 6e-3, tag
+            elif mode == 'aux':
+                aux = rnd(M, N, seed=3 * case + 3, dtype=torch.bfloat16)
+                C = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+                k.gemm_bf16(*args, C, N, aux=aux, ld_aux=N, aux_scale=1.25)
+                assert normwise(C, torch.where(aux.double() > 0, ref * 1.25, torch.zeros_like(ref))) < 6e-3, tag
+            else:
+                big = torch.zeros(M, N + 64, device=DEV, dtype=torch.bfloat16)
+                k.gemm_bf16(*args, big[:, 32:32 + N], N + 64)
+                assert normwise(big[:, 32:32 + N], ref) < 6e-3, tag
+                assert float(big[:, :32].abs().max()) == 0 and float(big[:, 32 + N:].abs().max()) == 0, tag
+    finally:
+        for var, val in prev.items():
+            if val is None:
+                os.environ.pop(var, None)
+            else:
+                os.environ[var] = val
