@@ -63,8 +63,10 @@ __device__ __forceinline__ uint32_t tile_t(uint32_t x) {
   return y;
 }
 
-template <bool BWD>
-__global__ void __launch_bounds__(THREADS, BWD ? 1 : 2) relbias_mma_kernel(MmaArgs a) {
+// MT = 16-pair M tiles per warp iteration: 2 in the forward; 1 in the backward, whose per-tile state (e fragments,
+// d e, geometry) would otherwise push it past 128 registers and down to one CTA per SM.
+template <bool BWD, int MT>
+__global__ void __launch_bounds__(THREADS, 2) relbias_mma_kernel(MmaArgs a) {
   __shared__ float4 sWy[R];            // W_y[c][0..3]
   __shared__ float sby[R];
   __shared__ float sred[R * HEADS + R * 4 + R + HEADS];     // dW_r | dW_y | db_y | db_r of this CTA
@@ -99,31 +101,32 @@ __global__ void __launch_bounds__(THREADS, BWD ? 1 : 2) relbias_mma_kernel(MmaAr
     for (int i = 0; i < 4; ++i) { accWr[m][i] = 0.f; accWy[m][i] = 0.f; }
   __syncthreads();
 
-  const unsigned iters = (a.pairs + 31u) >> 5;
+  constexpr unsigned PPI = 16u * MT;           // pairs per warp iteration
+  const unsigned iters = (a.pairs + PPI - 1u) / PPI;
   const unsigned stride = gridDim.x * WARPS;
   // geometry of the NEXT iteration's four pairs is fetched while the current one is processed
-  float4 gnext[2][2];
+  float4 gnext[MT][2];
   auto fetch_g = [&](unsigned wi_) {
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int rh = 0; rh < 2; ++rh) {
-        const unsigned p = (wi_ << 5) + 16 * mt + 8 * rh + g;
+        const unsigned p = wi_ * PPI + 16 * mt + 8 * rh + g;
         gnext[mt][rh] = (wi_ < iters && p < a.pairs) ? __ldg(reinterpret_cast<const float4*>(a.g4) + p) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
   };
   fetch_g(blockIdx.x * WARPS + warp);
   for (unsigned wi = blockIdx.x * WARPS + warp; wi < iters; wi += stride) {
-    const unsigned base = wi << 5;
-    // this thread's four pairs: M tile mt, row half rh -> base + 16 mt + 8 rh + g.  The 32 pairs of an iteration
+    const unsigned base = wi * PPI;
+    // this thread's pairs: M tile mt, row half rh -> base + 16 mt + 8 rh + g.  The pairs of an iteration
     // straddle few image boundaries: one integer division per iteration, then a short walk.
     const unsigned bb = base / a.nn, ij_base = base - bb * a.nn;
-    bool live[2][2];
-    size_t off[2][2];                    // element offset of (pair, head 2q) in bias / dbias
-    float4 gv[2][2];
-    float db[2][2][2];
+    bool live[MT][2];
+    size_t off[MT][2];                    // element offset of (pair, head 2q) in bias / dbias
+    float4 gv[MT][2];
+    float db[MT][2][2];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int rh = 0; rh < 2; ++rh) {
         const unsigned d = 16 * mt + 8 * rh + g;
@@ -141,13 +144,13 @@ __global__ void __launch_bounds__(THREADS, BWD ? 1 : 2) relbias_mma_kernel(MmaAr
     // ---- first layer on the FP32 pipe, straight into A-fragment registers (hi / lo bf16 pairs), and
     // ---- r = e W_r^T + b_r per M tile as soon as a 16-channel k-step is complete: accumulator rows g (rh 0) and
     // ---- g+8 (rh 1), columns = heads 2q, 2q+1.  The lo halves live for one k-step only.
-    uint32_t e_hi[2][2][8];
-    float rr[2][4];
+    uint32_t e_hi[MT][2][8];
+    float rr[MT][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) { rr[mt][0] = br0; rr[mt][1] = br1; rr[mt][2] = br0; rr[mt][3] = br1; }
+    for (int mt = 0; mt < MT; ++mt) { rr[mt][0] = br0; rr[mt][1] = br1; rr[mt][2] = br0; rr[mt][3] = br1; }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      uint32_t e_lo[2][2][2];
+      uint32_t e_lo[MT][2][2];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int n = 2 * k + j;
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(THREADS, BWD ? 1 : 2) relbias_mma_kernel(MmaAr
         const float4 w0 = sWy[c], w1 = sWy[c + 1];
         const float b0 = sby[c], b1 = sby[c + 1];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
           for (int rh = 0; rh < 2; ++rh) {
             const float4 v = gv[mt][rh];
@@ -165,7 +168,7 @@ __global__ void __launch_bounds__(THREADS, BWD ? 1 : 2) relbias_mma_kernel(MmaAr
           }
       }
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
+      for (int mt = 0; mt < MT; ++mt) {
         mma16816(rr[mt], e_hi[mt][0][2 * k], e_hi[mt][1][2 * k], e_hi[mt][0][2 * k + 1], e_hi[mt][1][2 * k + 1], wr_hi[k][0], wr_hi[k][1]);
         mma16816(rr[mt], e_lo[mt][0][0], e_lo[mt][1][0], e_lo[mt][0][1], e_lo[mt][1][1], wr_hi[k][0], wr_hi[k][1]);
         mma16816(rr[mt], e_hi[mt][0][2 * k], e_hi[mt][1][2 * k], e_hi[mt][0][2 * k + 1], e_hi[mt][1][2 * k + 1], wr_lo[k][0], wr_lo[k][1]);
@@ -173,7 +176,7 @@ __global__ void __launch_bounds__(THREADS, BWD ? 1 : 2) relbias_mma_kernel(MmaAr
     }
     if constexpr (!BWD) {
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int rh = 0; rh < 2; ++rh)
           if (live[mt][rh]) {
@@ -183,9 +186,9 @@ __global__ void __launch_bounds__(THREADS, BWD ? 1 : 2) relbias_mma_kernel(MmaAr
           }
     } else {
     // ---- backward
-    uint32_t dp[2][2];                   // d pre_r as A-fragment rows (K = heads 2q, 2q+1)
+    uint32_t dp[MT][2];                   // d pre_r as A-fragment rows (K = heads 2q, 2q+1)
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int rh = 0; rh < 2; ++rh) {
         const float r0 = rr[mt][2 * rh], r1 = rr[mt][2 * rh + 1];
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(THREADS, BWD ? 1 : 2) relbias_mma_kernel(MmaAr
         dp[mt][rh] = pack_bf16(d0, d1);
       }
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
+    for (int mt = 0; mt < MT; ++mt) {
       // d e = d pre_r W_r, masked by e > 0, as bf16 A-fragment tiles [pair rows][channels]
       uint32_t de[2][8];
 #pragma unroll
@@ -260,10 +263,10 @@ __global__ void __launch_bounds__(THREADS, BWD ? 1 : 2) relbias_mma_kernel(MmaAr
   if (tid < HEADS) atomicAdd(&a.dbr[tid], sbr[tid]);
 }
 
-int grid_for(unsigned pairs) {
-  const unsigned iters = (pairs + 31u) >> 5;
+int grid_for(unsigned pairs, unsigned pairs_per_iter, unsigned ctas_per_sm) {
+  const unsigned iters = (pairs + pairs_per_iter - 1u) / pairs_per_iter;
   const unsigned ctas = (iters + WARPS - 1) / WARPS;
-  return (int)(ctas < 148u * 2u ? ctas : 148u * 2u);      // persistent: <= 2 CTAs per SM
+  return (int)(ctas < 148u * ctas_per_sm ? ctas : 148u * ctas_per_sm);      // persistent: one resident wave
 }
 
 }  // namespace
@@ -275,7 +278,7 @@ int mmnas_relbias_fwd_mma(int B, int N, int heads, const float* g4, const float*
   MmaArgs a = {};
   a.nn = (unsigned)N * N; a.pairs = (unsigned)B * a.nn;
   a.g4 = g4; a.Wy = Wy; a.by = by; a.Wr = Wr; a.br = br; a.bias = bias;
-  MMNAS_CUDA(mmnas_launch(relbias_mma_kernel<false>, dim3(grid_for(a.pairs)), dim3(THREADS), 0, s, a));
+  MMNAS_CUDA(mmnas_launch(relbias_mma_kernel<false, 2>, dim3(grid_for(a.pairs, 32, 2)), dim3(THREADS), 0, s, a));
   return MMNAS_OK;
 }
 
@@ -287,6 +290,6 @@ int mmnas_relbias_bwd_mma(int B, int N, int heads, const float* g4, const float*
   a.nn = (unsigned)N * N; a.pairs = (unsigned)B * a.nn;
   a.g4 = g4; a.Wy = Wy; a.by = by; a.Wr = Wr; a.br = br; a.dbias = dbias;
   a.dWy = dWy; a.dby = dby; a.dWr = dWr; a.dbr = dbr;
-  MMNAS_CUDA(mmnas_launch(relbias_mma_kernel<true>, dim3(grid_for(a.pairs)), dim3(THREADS), 0, s, a));
+  MMNAS_CUDA(mmnas_launch(relbias_mma_kernel<true, 1>, dim3(grid_for(a.pairs, 16, 2)), dim3(THREADS), 0, s, a));
   return MMNAS_OK;
 }
