@@ -1,5 +1,6 @@
 """Process-wide runtime state of the operator path: precision mode and the dropout RNG state."""
 import itertools
+import os
 import threading
 
 import torch
@@ -10,7 +11,7 @@ _PRECISION = 'bf16'          # 'fp32' (FFMA kernels, 1e-5 parity arm) | 'bf16' (
 _rng_states = {}
 shadows_fresh = False      # True while an engine step guarantees that the managed bf16 weight shadows are current
 direct_grads = False       # True while an engine step wants block backwards to accumulate straight into p.grad
-overlap_wgrad = True       # run weight-gradient GEMMs on a side stream, concurrently with the dgrad / attention chain
+overlap_wgrad = os.environ.get('MMNAS_OVERLAP_WGRAD', '1') != '0'   # weight-gradient GEMMs on a side stream, concurrently with the dgrad / attention chain (env: ablation only)
 grad_listener = None       # callable(param): the data-parallel reducer's notification for directly written grads
 _salt_counter = itertools.count(1)
 _lock = threading.Lock()
