@@ -5,6 +5,7 @@ used for device memory and streams only; every argument crossing this boundary i
 pointer, a size or a scalar."""
 import ctypes
 import os
+import threading
 
 import torch
 
@@ -115,8 +116,21 @@ _raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
 _raw_device = getattr(torch._C, '_cuda_getDevice', None)
 
 
+_tls = threading.local()
+
+
+def set_stream_override(handle):
+    """Route this thread's C-ABI launches to the given cudaStream_t (None = back to torch's current stream).  Used for
+    the side-stream weight-gradient work of a block backward: cheaper than torch.cuda.stream() context switches on a
+    path that only launches library kernels."""
+    _tls.override = handle
+
+
 def stream():
     """cudaStream_t of torch's current stream on the current device (raw query: this sits on every launch path)."""
+    o = getattr(_tls, 'override', None)
+    if o is not None:
+        return o
     if _raw_stream is not None and _raw_device is not None:
         return _raw_stream(_raw_device())
     return torch.cuda.current_stream().cuda_stream

@@ -14,6 +14,7 @@ import math
 import torch
 from torch.autograd import Function
 
+from . import _lib
 from . import kernels as K
 from . import runtime
 from ._lib import require_cuda
@@ -77,6 +78,10 @@ def _grad_target(params):
     return torch.as_strided(g0, shape, tuple(params[0].stride()) if params[0].dim() > 1 else (1,))
 
 
+import os as _os
+_FORK_CTX = _os.environ.get('MMNAS_FORK_CTX', '0') == '1'     # A/B only: torch.cuda.stream() context instead of the launch-stream override
+
+
 class _Fork:
     """Weight-gradient work of one block backward on the side stream: `with fork:` enqueues there after everything
     issued so far on the main stream; join() makes the main stream wait for it (called before the backward returns,
@@ -89,18 +94,24 @@ class _Fork:
         if self.enabled:
             self.main = torch.cuda.current_stream(dev)
             self.side = runtime.side_stream(dev)
-            self.ctx = torch.cuda.stream(self.side)
 
-    def __enter__(self):
+    def __enter__(self):       # only library kernels are launched inside the block: redirect them, not torch's stream
         if self.enabled:
             self.side.wait_stream(self.main)
-            self.ctx.__enter__()
+            if _FORK_CTX:
+                self.ctx = torch.cuda.stream(self.side)
+                self.ctx.__enter__()
+            else:
+                _lib.set_stream_override(self.side.cuda_stream)
             self.used = True
         return self
 
     def __exit__(self, *a):
         if self.enabled:
-            self.ctx.__exit__(*a)
+            if _FORK_CTX:
+                self.ctx.__exit__(*a)
+            else:
+                _lib.set_stream_override(None)
         return False
 
     def join(self):
