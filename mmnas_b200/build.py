@@ -24,19 +24,35 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """Compile every .cu for sm_100a (one nvcc process per source, in parallel) and link the shared library."""
     if not force and not needs_build():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    objdir = os.path.join(os.path.dirname(LIB), 'obj')
+    os.makedirs(objdir, exist_ok=True)
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    flags = [f for f in NVCC_FLAGS if f != '--use_fast_math=false']
-    cmd = [nvcc] + flags + ['-o', LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
+    flags = [f for f in NVCC_FLAGS if f not in ('--use_fast_math=false', '-shared')]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace('.cu', '.o'))
+        r = subprocess.run([nvcc] + flags + ['-c', '-o', obj, os.path.join(CSRC, src)], capture_output=True, text=True)
+        return src, obj, r
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    log = ''.join('== %s\n%s%s' % (src, r.stdout, r.stderr) for src, _, r in results)
+    failed = [src for src, _, r in results if r.returncode != 0]
+    if verbose or failed:
+        sys.stderr.write(log)
+    if failed:
+        raise RuntimeError('nvcc failed on %s' % ', '.join(failed))
+    r = subprocess.run([nvcc, '-shared', '-o', LIB] + [obj for _, obj, _ in results], capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError('nvcc failed building libmmnas_b200.so')
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError('linking libmmnas_b200.so failed')
     with open(os.path.join(os.path.dirname(LIB), 'ptxas.log'), 'w') as f:
-        f.write(r.stdout + r.stderr)
+        f.write(log)
     return LIB
 
 

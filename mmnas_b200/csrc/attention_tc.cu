@@ -9,7 +9,7 @@
 //             P (bf16, dropout applied) -> shared memory in the canonical K-major 128B-swizzled UMMA layout
 //             O = P V            (A = P K-major, B = V as an MN-major operand straight from its TMA tile)
 //   backward  S = Q K^T, dP = dO V^T                       (V's tile re-read as a K-major operand)
-//             dS = P (m dP - delta), delta_i = dO_i . O_i ;  Pd, dS -> shared memory once, as [i][j] bf16
+//             dS = P (m dP - delta), delta_i = dO_i . O_i = sum_j P_ij m_ij dP_ij (fp32, from TMEM);  Pd, dS -> shared memory once, as [i][j] bf16
 //             dV = Pd^T dO, dK = dS^T Q   (the same tiles read as MN-major A operands: no transposes)
 //             dQ = dS K
 // Q, K, V, dO tiles (128 rows x 64 head columns) arrive by TMA directly from the fused projection buffers
@@ -304,23 +304,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   }
   const int i = tid;
   const bool row_ok = i < Nq;
-  // delta_i = dO_i . O_i from global while the MMAs run
-  float delta = 0.f;
-  if (row_ok) {
-    const uint4* orow = reinterpret_cast<const uint4*>(a.o + ((size_t)b * Nq + i) * a.ldo + h * 64);
-    const uint4* drow = reinterpret_cast<const uint4*>(a.dout + ((size_t)b * Nq + i) * a.lddo + h * 64);
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const uint4 ov = __ldg(orow + g), dv = __ldg(drow + g);
-      const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov);
-      const __nv_bfloat162* d2 = reinterpret_cast<const __nv_bfloat162*>(&dv);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float2 of = __bfloat1622float2(o2[u]), df = __bfloat1622float2(d2[u]);
-        delta = fmaf(of.x, df.x, fmaf(of.y, df.y, delta));
-      }
-    }
-  }
   mbar_wait(bar + 8, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
@@ -328,29 +311,50 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   const bool use_drop = a.drop.state != nullptr && a.drop.thresh > 0;
   const uint64_t key = use_drop ? drop_key(a.drop) : 0;
   const RowCtx ctx = make_row_ctx(a, b, h, i, row_ok, tid & 31);
-  float mx = -INFINITY, sum = 0.f;
+  // pass 1: row maximum, row sum and delta_i = dO_i . O_i = sum_j P_ij m_ij dP_ij together (running rescale).
+  // delta is formed in fp32 from the TMEM-resident S and dP, i.e. from the SAME probabilities the dS pass uses, so
+  // sum_j dS_ij cancels to fp32 rounding.  (Taking it from the bf16-rounded O and dO in global memory left a
+  // residue of ~2^-9 |delta| in every row sum, which is what d linear_r.bias = sum dS / r accumulates.)
+  float mx = -INFINITY, sum = 0.f, num = 0.f;
 #pragma unroll 1
-  for (int cc = 0; cc < NC; ++cc) {                 // pass 1: row maximum and row sum together (running rescale)
-    uint32_t r[32];
+  for (int cc = 0; cc < NC; ++cc) {
+    uint32_t r[32], rp[32];
     float s[32], bb[32];
     chunk_bias<VEC>(a, ctx, cc, bb);
-    tmem_ld32(trow + cc * 32, r);
+    tmem_ld32_nowait(trow + cc * 32, r);
+    tmem_ld32_nowait(trow + 128 + cc * 32, rp);
+    tmem_ld_wait();
     chunk_logits(a, ctx, cc, r, bb, s);
     float cm = s[0];
 #pragma unroll
     for (int t = 1; t < 32; ++t) cm = fmaxf(cm, s[t]);
     const float nm = fmaxf(mx, cm);                 // finite from chunk 0 on: key 0 is never -inf
     const float nml = nm * LOG2E;
-    float part = 0.f;
+    float part = 0.f, pnum = 0.f;
 #pragma unroll
-    for (int t = 0; t < 32; ++t) part += exp2f(fmaf(s[t], LOG2E, -nml));
+    for (int g = 0; g < 8; ++g) {
+      float m[4] = {1.f, 1.f, 1.f, 1.f};
+      if (use_drop && cc * 32 + 4 * g < Nk) drop4<VEC>(a, ctx, key, cc * 32 + 4 * g, m);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = 4 * g + u;
+        const float e = exp2f(fmaf(s[t], LOG2E, -nml));
+        part += e;
+        // dP columns past Nk were never written by the MMA (TMEM garbage, possibly NaN): select, do not multiply
+        const float dp = (cc * 32 + t < Nk) ? __uint_as_float(rp[t]) : 0.f;
+        pnum = fmaf(e * m[u], dp, pnum);
+      }
+    }
     // rescale by exactly the ratio of the two term scalings (1 when the maximum did not move, even at -1e9 where
     // the rounded products carry errors of +-64; 0 on the first chunk, mx = -inf)
-    sum = fmaf(sum, exp2f(__fmul_rn(mx, LOG2E) - nml), part);      // __fmul_rn: no contraction into an fma
+    const float f = exp2f(__fmul_rn(mx, LOG2E) - nml);             // __fmul_rn: no contraction into an fma
+    sum = fmaf(sum, f, part);
+    num = fmaf(num, f, pnum);
     mx = nm;
   }
   const float mxl = mx * LOG2E;
   const float inv = (row_ok && sum > 0.f) ? 1.f / sum : 0.f;     // rows >= Nq contribute zeros to dK / dV
+  const float delta = num * inv;
   float* dbrow = (a.dbias && row_ok) ? a.dbias + ctx.rowbase : nullptr;
 #pragma unroll 1
   for (int cc = 0; cc < NC; ++cc) {                 // pass 2: P (dropped), dS -> shared memory; d bias -> global

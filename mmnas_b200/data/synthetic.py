@@ -37,24 +37,89 @@ def random_boxes(n, gen, img_w=640., img_h=480.):
     return torch.stack((x1, y1, x1 + w, y1 + h), dim=1)
 
 
-def make_batch(spec, seed=888):
-    """One host batch (CPU tensors).  Returns (input_tuple, target)."""
-    g = torch.Generator().manual_seed(seed)
-    B, N, T = spec.batch, spec.n_regions, spec.n_tokens
-    frcn = torch.relu(torch.randn(B, N, spec.feat, generator=g))
+def _box_iou(boxes, gt):
+    """IoU of boxes [n,4] with one box gt [4] (the +1 pixel convention of the reference's bbox_overlaps, bbox.pyx)."""
+    iw = (torch.minimum(boxes[:, 2], gt[2]) - torch.maximum(boxes[:, 0], gt[0]) + 1).clamp(min=0)
+    ih = (torch.minimum(boxes[:, 3], gt[3]) - torch.maximum(boxes[:, 1], gt[1]) + 1).clamp(min=0)
+    area = (boxes[:, 2] - boxes[:, 0] + 1) * (boxes[:, 3] - boxes[:, 1] + 1)
+    ga = (gt[2] - gt[0] + 1) * (gt[3] - gt[1] + 1)
+    inter = iw * ih
+    return inter / (area + ga - inter)
+
+
+def _box_deltas(boxes, gt):
+    """Fast-RCNN regression targets of gt w.r.t. every box (bbox_transform.py), normalised like BBOX_NORM does."""
+    w, h = boxes[:, 2] - boxes[:, 0] + 1, boxes[:, 3] - boxes[:, 1] + 1
+    cx, cy = boxes[:, 0] + 0.5 * w, boxes[:, 1] + 0.5 * h
+    gw, gh = gt[2] - gt[0] + 1, gt[3] - gt[1] + 1
+    gx, gy = gt[0] + 0.5 * gw, gt[1] + 0.5 * gh
+    d = torch.stack(((gx - cx) / w, (gy - cy) / h, torch.log(gw / w), torch.log(gh / h)), dim=1)
+    return d / torch.tensor([0.1, 0.1, 0.2, 0.2])
+
+
+def _regions(B, N, feat, ragged, g):
+    frcn = torch.relu(torch.randn(B, N, feat, generator=g))
     bbox = torch.zeros(B, N, 5)
     rel_img = torch.zeros(B, N, N, 4)
-    ques = torch.zeros(B, T, dtype=torch.int64)
+    boxes_all = []
     for b in range(B):
-        n_obj = int(torch.randint(10, N + 1, (1,), generator=g)) if (spec.ragged and N >= 10) else N
+        n_obj = int(torch.randint(10, N + 1, (1,), generator=g)) if (ragged and N >= 10) else N
         frcn[b, n_obj:] = 0
         boxes = random_boxes(n_obj, g)
         rel_img[b, :n_obj, :n_obj] = box_geometry(boxes)
         bbox[b, :n_obj, :4] = boxes / torch.tensor([640., 480., 640., 480.])
         bbox[b, :n_obj, 4] = ((boxes[:, 2] - boxes[:, 0]) * (boxes[:, 3] - boxes[:, 1])) / (640. * 480.)
-        lo = min(3, T)
-        n_tok = int(torch.randint(lo, T + 1, (1,), generator=g)) if spec.ragged else T
-        ques[b, :n_tok] = torch.randint(3, spec.vocab, (n_tok,), generator=g)
+        boxes_all.append(boxes)
+    return frcn, bbox, rel_img, boxes_all
+
+
+def _tokens(B, T, vocab, lo, hi, g):
+    ques = torch.zeros(B, T, dtype=torch.int64)
+    for b in range(B):
+        n_tok = int(torch.randint(lo, hi + 1, (1,), generator=g))
+        ques[b, :n_tok] = torch.randint(3, vocab, (n_tok,), generator=g)
+    return ques
+
+
+def make_batch(spec, seed=888):
+    """One host batch (CPU tensors).  Returns (input_tuple, target).
+
+    vqa: target = ans [B, n_ans] soft scores                                         (load_data_vqa.py:221-275)
+    vgd: every region valid, queries of n_tokens (= 15: max_token + 1, the last slot always 0); target =
+         (scores [B,N] IoU-proportional over regions with IoU >= 0.5, scores_mask [B,1], transformed_bbox [B,N,4],
+         bbox_mask [B,N,1])                                                          (load_data_vgd.py:175-186,241-283)
+    itm: the three forwards of a step stacked along the batch: rows [0,B) positive pairs, [B,2B) the same images with
+         negative captions, [2B,3B) negative images with the positive captions (train_itm.py:380-389); target = None."""
+    g = torch.Generator().manual_seed(seed)
+    B, N, T = spec.batch, spec.n_regions, spec.n_tokens
+    if spec.task == 'vgd':
+        frcn, bbox, rel_img, boxes_all = _regions(B, N, spec.feat, False, g)
+        ques = _tokens(B, T, spec.vocab, min(3, T - 1), T - 1, g)
+        scores, smask = torch.zeros(B, N), torch.zeros(B, 1)
+        tbox, bmask = torch.zeros(B, N, 4), torch.zeros(B, N, 1)
+        for b, boxes in enumerate(boxes_all):
+            k = int(torch.randint(0, boxes.shape[0], (1,), generator=g))
+            gt = boxes[k] + 6 * torch.randn(4, generator=g)          # the referred object: a jittered region box
+            gt = torch.stack((torch.minimum(gt[0], gt[2] - 4), torch.minimum(gt[1], gt[3] - 4), gt[2], gt[3]))
+            iou = _box_iou(boxes, gt)
+            hit = iou >= 0.5
+            if bool(hit.any()):
+                smask[b] = 1
+                sc = torch.where(hit, iou, torch.zeros_like(iou))
+                scores[b, :boxes.shape[0]] = sc / (sc.sum() + 1e-8)
+                bmask[b, :boxes.shape[0], 0] = hit.float()
+            tbox[b, :boxes.shape[0]] = _box_deltas(boxes, gt)
+        return (frcn, bbox, rel_img, ques, torch.zeros(B, T, T, 3)), (scores, smask, tbox, bmask)
+    if spec.task == 'itm':
+        frcn, bbox, rel_img, _ = _regions(2 * B, N, spec.feat, spec.ragged, g)      # positive and negative images
+        caps = _tokens(2 * B, T, spec.vocab, min(5, T), min(30, T), g)              # positive and negative captions
+        pos, neg = slice(0, B), slice(B, 2 * B)
+        cat = lambda t, order: torch.cat([t[o] for o in order], 0)                  # noqa: E731
+        img_order, cap_order = (pos, pos, neg), (pos, neg, pos)
+        return ((cat(frcn, img_order), cat(bbox, img_order), cat(rel_img, img_order), cat(caps, cap_order),
+                 torch.zeros(3 * B, T, T, 3)), torch.zeros(1))
+    frcn, bbox, rel_img, _ = _regions(B, N, spec.feat, spec.ragged, g)
+    ques = _tokens(B, T, spec.vocab, min(3, T), T, g) if spec.ragged else torch.randint(3, spec.vocab, (B, T), generator=g)
     rel_ques = torch.zeros(B, T, T, 3)
     levels = torch.tensor([0., .3, .6, .9, 1.])
     ans = torch.zeros(B, spec.n_ans)
@@ -63,6 +128,15 @@ def make_batch(spec, seed=888):
         idx = torch.randint(0, spec.n_ans, (k,), generator=g)
         ans[b, idx] = levels[torch.randint(1, 5, (k,), generator=g)]
     return (frcn, bbox, rel_img, ques, rel_ques), ans
+
+
+def spec_for(task, batch=64, **over):
+    """The BASELINE shapes of each task (T/S 100 regions x 14 tokens; G 100 x 15; I 36 x 50)."""
+    if task == 'vgd':
+        return SynthSpec(task='vgd', batch=batch, n_regions=100, n_tokens=15, ragged=False, **over)
+    if task == 'itm':
+        return SynthSpec(task='itm', batch=batch, n_regions=36, n_tokens=50, **over)
+    return SynthSpec(task='vqa', batch=batch, **over)
 
 
 def init_dict(spec, seed=888):

@@ -282,7 +282,49 @@ class FusedClipAdam:
 
 # ------------------------------------------------------------------------------------------------ steps
 def vqa_loss(pred, target):
+    """train_vqa.py:297: BCEWithLogitsLoss(reduction='sum')."""
     return F.binary_cross_entropy_with_logits(pred, target, reduction='sum')
+
+
+def vgd_loss(pred, target, loss_lambda=0.5):
+    """train_vgd.py:320-334 with the shipped settings (SCORES_LOSS 'kld', LOSS_AVG True, LOSS_LAMBDA 0.5, REDUCTION
+    'sum'): KLDivLoss over the masked log-softmax region scores / #scored samples + 0.5 * SmoothL1 over the masked box
+    regressions / #matching regions.  target = (scores, scores_mask, transformed_bbox, bbox_mask)."""
+    pred_scores, pred_reg = pred
+    scores, scores_mask, tbox, bbox_mask = target
+    loss_scores = F.kl_div(pred_scores * scores_mask, scores * scores_mask, reduction='sum')
+    loss_reg = F.smooth_l1_loss(pred_reg * bbox_mask, tbox * bbox_mask, reduction='sum')
+    return loss_scores / scores_mask.sum() + loss_lambda * (loss_reg / bbox_mask.sum())
+
+
+def itm_loss(pred, target=None):
+    """mmnas/utils/itm_loss.py:13-24 (BCE_Loss, reduction 'sum'): loss_pos + loss_negc + loss_pos + loss_negi — the
+    positive term is counted twice, as in the reference.  `pred` holds the sigmoid scores of the three forwards of
+    train_itm.py:387-389 stacked along the batch: [positive | negative captions | negative images]."""
+    pos, negc, negi = pred.chunk(3, dim=0)
+    one, zero = torch.ones_like(pos), torch.zeros_like(pos)
+    bce = F.binary_cross_entropy
+    return 2.0 * bce(pos, one, reduction='sum') + bce(negc, zero, reduction='sum') + bce(negi, zero, reduction='sum')
+
+
+LOSSES = {'vqa': vqa_loss, 'vgd': vgd_loss, 'itm': itm_loss}
+
+
+def tree_map(fn, obj):
+    """Apply fn to every tensor of a (nested) tuple / list; None passes through."""
+    if obj is None:
+        return None
+    if torch.is_tensor(obj):
+        return fn(obj)
+    return tuple(tree_map(fn, o) for o in obj)
+
+
+def tree_leaves(obj):
+    if obj is None:
+        return []
+    if torch.is_tensor(obj):
+        return [obj]
+    return [t for o in obj for t in tree_leaves(o)]
 
 
 class TrainStep:
@@ -305,7 +347,7 @@ class TrainStep:
     def _body(self, inputs, target):
         self.grads.zero()
         self.reducer.reset()
-        runtime.advance(target.device)
+        runtime.advance(self.grads.flat.device)
         if runtime.get_precision() == 'bf16':
             self.shadows.refresh()
             runtime.shadows_fresh = True
@@ -327,20 +369,36 @@ class TrainStep:
             return self._body(inputs, target)
         if self.graph is None:
             self._capture(inputs, target)
-        for dst, src in zip(self._static_in, inputs):
+        for dst, src in zip(tree_leaves(self._static_in) + tree_leaves(self._static_tgt),
+                            tree_leaves(inputs) + tree_leaves(target)):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
-        if self._static_tgt.data_ptr() != target.data_ptr():
-            self._static_tgt.copy_(target, non_blocking=True)
         self.graph.replay()
         return self._static_loss
 
+    def _mutable_state(self):
+        """Every tensor a step mutates: parameters, Adam moments + step counter, the dropout step counter.  (Gradients
+        and bf16 shadows are rewritten from scratch by each step.)"""
+        st = list(self.grads.params)
+        f = self.optim.fused
+        st += [f.exp_avg, f.exp_avg_sq, f.state]
+        st.append(runtime.rng_state(self.grads.flat.device))
+        return st
+
     def _capture(self, inputs, target):
-        self._static_in = tuple(t.clone() for t in inputs)
-        self._static_tgt = target.clone()
+        """Warm up (allocator pools, lazy initialisation) and capture the step.  The warm-up steps run on the first
+        batch; everything they mutate is snapshotted before and restored after, so the FIRST replay is the first
+        update — graph and eager runs evolve identically (parameters, Adam moments, bias-correction count, dropout
+        step counter)."""
+        self._static_in = tree_map(torch.clone, inputs)
+        self._static_tgt = tree_map(torch.clone, target)
+        if self.optim.fused is None:
+            raise RuntimeError('graph capture needs CUDA parameters (fused clip + Adam)')
+        state = self._mutable_state()
+        saved = [t.detach().clone() for t in state]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):               # warm-up outside capture (allocator, Adam state, lazy init)
+        with torch.cuda.stream(side):               # warm-up outside capture
             for _ in range(3):
                 self._body(self._static_in, self._static_tgt)
         torch.cuda.current_stream().wait_stream(side)
@@ -348,6 +406,10 @@ class TrainStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self._static_loss = self._body(self._static_in, self._static_tgt)
+        with torch.no_grad():                       # capture executes nothing, the warm-up did: undo it
+            for t, v in zip(state, saved):
+                t.copy_(v)
+        torch.cuda.synchronize()
 
     @property
     def static_inputs(self):
@@ -375,7 +437,7 @@ class SearchStep:
     def _forward_backward(self, inputs, target):
         self.grads.zero()                # net.zero_grad() + the reference's 0*sum(params) dummy terms
         self.reducer.reset()
-        runtime.advance(target.device)
+        runtime.advance(self.grads.flat.device)
         if runtime.get_precision() == 'bf16':
             self.shadows.refresh()
             runtime.shadows_fresh = True
@@ -438,19 +500,17 @@ class Prefetcher:
 
     @staticmethod
     def _flat(batch):
-        inputs, target = batch
-        return list(inputs) + [target]
+        return tree_leaves(batch)
 
     def _pin(self, batch):
-        inputs, target = batch
-        return tuple(t.pin_memory() for t in inputs), target.pin_memory()
+        return tree_map(lambda t: t.pin_memory(), batch)
 
     def _issue(self):
         inputs, target = self.host[self._i % len(self.host)]
         self._i += 1
         with torch.cuda.stream(self.stream):
-            dev_in = tuple(t.to(self.device, non_blocking=True) for t in inputs)
-            dev_tgt = target.to(self.device, non_blocking=True)
+            dev_in = tree_map(lambda t: t.to(self.device, non_blocking=True), inputs)
+            dev_tgt = tree_map(lambda t: t.to(self.device, non_blocking=True), target)
         self._next = (dev_in, dev_tgt)
 
     def next(self):

@@ -204,28 +204,46 @@ class Net_Search(_NetBase):
             self._redundant_modules = [m for m in self.modules() if str(m).startswith('MixedOp')]
         return self._redundant_modules
 
-    def reset_binary_gates(self, batched=False):
-        """Sample every node's active path (MixedOp.binarize, mixed.py:131-163).  batched=True draws all nodes of
-        equal width with ONE multinomial call and ONE host read (2 syncs per step instead of 30) and leaves the
-        candidates' .grad buffers alone — the step harness zeroes the flat gradient buffer, which is what the
-        reference's dummy-loss terms turn the None grads into anyway.  Not for MODE 'two'."""
+    def reset_binary_gates(self, batched=False, group=None):
+        """Sample every node's active path (MixedOp.binarize, mixed.py:131-163).
+
+        batched=True (the step harness) keeps the reference's random-number consumption — one
+        `torch.multinomial(probs, 1)` per MixedOp, in module registration order, on a [K] probability vector, exactly
+        the call sequence of hygr_vqa.py:168-172 over mixed.py:151 — so one seed draws the same path as the reference.
+        Only the bookkeeping around the draws is batched: one softmax per node width, ONE host read of all 30 picks
+        (instead of 30 `.item()` syncs), one multi-tensor copy for the one-hot gates, and the candidates' .grad buffers
+        are left alone (the harness zeroes the flat gradient buffer, which is what the reference's dummy-loss terms turn
+        the None grads into anyway).  Under data parallelism the picks are broadcast from rank 0, so every rank runs
+        the same path by construction (the reference relies on identically seeded ranks).  Not for MODE 'two'."""
         if not batched:
             for m in self.redundant_modules:
                 m.binarize()
             return
-        groups = {}
-        for m in self.redundant_modules:
-            groups.setdefault(m.n_choices, []).append(m)
+        mods = self.redundant_modules
         with torch.no_grad():
-            for k, mods in groups.items():
-                probs = F.softmax(torch.stack([m.alpha_prob.data for m in mods]), dim=1)
-                picks = torch.multinomial(probs, 1).squeeze(1)
-                onehot = F.one_hot(picks, k).to(probs.dtype)
-                idx = picks.tolist()
-                for m, a, g in zip(mods, idx, onehot):
-                    m.alpha_gate.data.copy_(g)
-                    m.active_index = [a]
-                    m.inactive_index = [i for i in range(k) if i != a]
+            rows = {}
+            groups = {}
+            for m in mods:
+                groups.setdefault(m.n_choices, []).append(m)
+            for k, ms in groups.items():
+                probs = F.softmax(torch.stack([m.alpha_prob.data for m in ms]), dim=1)
+                for m, p in zip(ms, probs.unbind(0)):
+                    rows[id(m)] = p
+            picks = torch.cat([torch.multinomial(rows[id(m)], 1) for m in mods])
+            if group is not False and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                    and torch.distributed.get_world_size(group) > 1:
+                torch.distributed.broadcast(picks, 0, group=group)
+            idx = picks.tolist()
+            gates, onehots = [], []
+            pos = {id(m): i for i, m in enumerate(mods)}
+            for k, ms in groups.items():
+                oh = F.one_hot(picks[torch.tensor([pos[id(m)] for m in ms], device=picks.device)], k).to(ms[0].alpha_gate.dtype)
+                gates += [m.alpha_gate.data for m in ms]
+                onehots += list(oh.unbind(0))
+            torch._foreach_copy_(gates, onehots)
+            for m, a in zip(mods, idx):
+                m.active_index = [a]
+                m.inactive_index = [i for i in range(m.n_choices) if i != a]
 
     def unused_modules_off(self):
         self._unused_modules = []

@@ -303,6 +303,75 @@ def train_step_vqa(P, inputs, target, genotype, p=0.0, training=False):
     return loss.detach(), pred.detach()
 
 
+def vgd_loss(pred_scores, pred_reg, scores, scores_mask, transformed_bbox, bbox_mask, loss_lambda=0.5):
+    """train_vgd.py:320-334 with the shipped configuration (SCORES_LOSS 'kld' :159, LOSS_AVG True :160, LOSS_LAMBDA
+    0.5 :161, REDUCTION 'sum' :178): KLDivLoss(sum) over masked log-probabilities :323, SmoothL1Loss(sum) over masked
+    box deltas :324, each divided by its mask count :327-333."""
+    loss_scores = F.kl_div(pred_scores * scores_mask, scores * scores_mask, reduction='sum')
+    loss_reg = F.smooth_l1_loss(pred_reg * bbox_mask, transformed_bbox * bbox_mask, reduction='sum')
+    return loss_scores / scores_mask.sum() + loss_lambda * (loss_reg / bbox_mask.sum())
+
+
+def itm_bce_loss(scores_pos, scores_negc, scores_negi):
+    """mmnas/utils/itm_loss.py:13-24 (BCE_Loss, REDUCTION 'sum' train_itm.py:171): loss_pos + loss_negc + loss_pos +
+    loss_negi — the positive term counted twice (:22), kept literally."""
+    loss_pos = F.binary_cross_entropy(scores_pos, torch.ones_like(scores_pos), reduction='sum')
+    loss_negc = F.binary_cross_entropy(scores_negc, torch.zeros_like(scores_negc), reduction='sum')
+    loss_negi = F.binary_cross_entropy(scores_negi, torch.zeros_like(scores_negi), reduction='sum')
+    return loss_pos + loss_negc + loss_pos + loss_negi
+
+
+def train_step_vgd(P, inputs, target, genotype, p=0.0, training=False):
+    """Loss + grads of the VGD step body train_vgd.py:317-335."""
+    pred_scores, pred_reg = net_full(P, inputs, genotype, task='vgd', scores_loss='kld', p=p, training=training)
+    loss = vgd_loss(pred_scores, pred_reg, *target)
+    loss.backward()
+    return loss.detach(), (pred_scores.detach(), pred_reg.detach())
+
+
+def train_step_itm(P, input_pos, input_negc, input_negi, genotype, p=0.0, training=False):
+    """Loss + grads of the ITM step body train_itm.py:384-392: THREE forwards of the same net, then BCE_Loss."""
+    s_pos = net_full(P, input_pos, genotype, task='itm', p=p, training=training)
+    s_negc = net_full(P, input_negc, genotype, task='itm', p=p, training=training)
+    s_negi = net_full(P, input_negi, genotype, task='itm', p=p, training=training)
+    loss = itm_bce_loss(s_pos, s_negc, s_negi)
+    loss.backward()
+    return loss.detach(), (s_pos.detach(), s_negc.detach(), s_negi.detach())
+
+
+def binarize_two(alpha_prob, generator=None):
+    """MixedOp.binarize in MODE 'two' (mixed.py:136-148): draw two candidates without replacement from
+    softmax(alpha_prob), then pick the active one of the pair from the softmax over just those two alphas."""
+    probs = F.softmax(alpha_prob.detach(), dim=0)
+    pair = torch.multinomial(probs, 2, replacement=False, generator=generator)
+    sub = F.softmax(torch.stack([alpha_prob.detach()[i] for i in pair]), dim=0)
+    c = torch.multinomial(sub, 1, generator=generator)[0]
+    return pair[c].item(), pair[1 - c].item()
+
+
+def arch_param_grad_two(alpha_prob, gate_grad, active, inactive):
+    """MixedOp.set_arch_param_grad in MODE 'two' (mixed.py:179-186): the 2 x 2 rule over the involved pair only."""
+    involved = [active, inactive]
+    probs = F.softmax(torch.stack([alpha_prob.detach()[i] for i in involved]), dim=0)
+    out = torch.zeros_like(alpha_prob.detach())
+    for i in range(2):
+        for j in range(2):
+            out[involved[i]] += gate_grad[involved[j]] * probs[j] * ((1 if i == j else 0) - probs[i])
+    return out
+
+
+def rescale_two(alpha_new, alpha_old, active, inactive):
+    """MixedOp.rescale_updated_arch_param (mixed.py:200-208): shift the two touched alphas so that their logsumexp is
+    what it was before the optimizer step."""
+    involved = [active, inactive]
+    offset = math.log(sum(math.exp(float(alpha_new[i])) for i in involved) /
+                      sum(math.exp(float(alpha_old[i])) for i in involved))
+    out = alpha_new.detach().clone()
+    for i in involved:
+        out[i] -= offset
+    return out
+
+
 def clip_and_adam(params, state, step, lr, max_norm=1.0, betas=(0.9, 0.98), eps=1e-9):
     """clip_grad_norm_ (train_vqa.py:310) then Adam (train_vqa.py:311 via optimizer.py:14-20), in place."""
     grads = [p.grad for p in params if p.grad is not None]

@@ -1,0 +1,96 @@
+"""Worker of tests/test_gpu_reference_dropin.py (run as a subprocess, one per implementation).
+
+    python tests/_dropin_worker.py {ours|ref} OUT.pt
+
+Imports the UNMODIFIED reference callers from baseline/_ref (mmnas/model/full_vqa.py, hygr_vqa.py — populated by
+scripts/install_reference.py) and runs, on cuda:0 in float32:
+  1. full_vqa.Net_Full with the genotype read from baseline/_ref/arch/mmnas_vqa.json exactly as train_vqa.py:185 does,
+     one train-step body (train_vqa.py:294-299): logits, loss, every parameter gradient;
+  2. hygr_vqa.Net_Search, one architecture-step body in MODE 'full' (search_vqa.py:317-331) driven through the
+     reference's own bookkeeping (reset_binary_gates / unused_modules_off / set_arch_param_grad / genotype).
+With `ours`, mmnas_b200.install_as_mmnas() first replaces mmnas.model.modules, mmnas.model.mixed and
+mmnas.utils.ops_adapter, so the reference's nets run on this library's CUDA operators; with `ref` nothing is replaced."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, 'baseline', '_ref')
+
+
+def main():
+    impl, out_path = sys.argv[1], sys.argv[2]
+    sys.path.insert(0, ROOT)
+    sys.path.insert(1, REF)
+    torch.backends.cudnn.allow_tf32 = False           # the callers' cuDNN LSTM in true fp32 for both implementations
+    torch.backends.cuda.matmul.allow_tf32 = False
+    if impl == 'ours':
+        import mmnas_b200
+        mmnas_b200.install_as_mmnas()
+        mmnas_b200.set_precision('fp32')
+    from mmnas.model.full_vqa import Net_Full
+    from mmnas.model.hygr_vqa import Net_Search
+    from mmnas.model.mixed import MixedOp
+    import mmnas.model.modules as M
+    from mmnas_b200.data.synthetic import Cfg, SynthSpec, make_batch, init_dict
+    from tests.util import condition_rsa_
+    dev = 'cuda:0'
+    res = {'modules': M.__name__}
+
+    # ---- 1. train-time net from the reference's arch JSON
+    geno = json.load(open(os.path.join(REF, 'arch', 'mmnas_vqa.json')))['epoch0']      # train_vqa.py:185
+    spec = SynthSpec(batch=4, vocab=1000, n_ans=100)
+    cfg = Cfg(genotype=geno, DROPOUT_R=0.0)
+    inputs, target = make_batch(spec, 888)
+    torch.manual_seed(888)
+    net = Net_Full(cfg, init_dict(spec))
+    with torch.no_grad():
+        condition_rsa_(dict(net.named_parameters()))
+    net = net.to(dev).train()
+    pred = net(tuple(t.to(dev) for t in inputs))
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(pred, target.to(dev), reduction='sum')
+    loss = loss + 0 * sum(p.sum() for p in net.parameters())                           # train_vqa.py:298
+    loss.backward()
+    res['full'] = {'pred': pred.detach().cpu(), 'loss': loss.detach().cpu(),
+                   'grads': {n: p.grad.detach().cpu() for n, p in net.named_parameters()},
+                   'keys': {k: tuple(v.shape) for k, v in net.state_dict().items()}}
+    del net, pred, loss
+
+    # ---- 2. supernet, MODE 'full' architecture step through the reference's own Net_Search methods
+    cfg = Cfg(mode='search', DROPOUT_R=0.0)
+    torch.manual_seed(888)
+    net = Net_Search(cfg, init_dict(spec))
+    with torch.no_grad():
+        condition_rsa_(dict(net.named_parameters()))
+    net = net.to(dev).train()
+    MixedOp.MODE = 'full'
+    torch.manual_seed(888)
+    net.reset_binary_gates()
+    net.unused_modules_off()
+    picks = [m.active_index[0] for m in net.redundant_modules]
+    pred = net(tuple(t.to(dev) for t in inputs))
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(pred, target.to(dev), reduction='sum')
+    loss = loss + 0 * sum(p.sum() for p in net.alpha_prob_parameters())                # search_vqa.py:321-323
+    loss = loss + 0 * sum(p.sum() for p in net.alpha_gate_parameters())
+    loss = loss + 0 * sum(p.sum() for p in net.net_parameters())
+    net.zero_grad()
+    loss.backward()
+    gate = {n: p.grad.detach().cpu().clone() for n, p in net.named_alpha_gate_parameters()}
+    net.set_arch_param_grad()
+    prob = {n: p.grad.detach().cpu().clone() for n, p in net.named_alpha_prob_parameters()}
+    net.unused_modules_back()
+    MixedOp.MODE = None
+    res['search'] = {'picks': picks, 'pred': pred.detach().cpu(), 'loss': loss.detach().cpu(), 'gate': gate, 'prob': prob,
+                     'genotype': net.genotype(),
+                     'grads': {n: p.grad.detach().cpu() for n, p in net.named_net_parameters() if p.grad is not None}}
+    if impl == 'ours':
+        from mmnas_b200 import _lib
+        res['launches'] = _lib.LAUNCHES
+    torch.save(res, out_path)
+
+
+if __name__ == '__main__':
+    main()

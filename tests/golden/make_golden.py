@@ -234,6 +234,124 @@ def golden_net_search(mods):
     np.savez_compressed(os.path.join(OUT, 'net_search_h64.npz'), **npify(rec))
 
 
+def golden_mixed_two(mods):
+    """MixedOp in MODE 'two' (mixed.py:136-148, :179-191, :200-208): the pair binarize() draws under seed 888, the
+    gated two-candidate output, alpha_gate.grad, the 2 x 2 alpha_prob.grad rule, one alpha Adam step (lr 0.1,
+    betas (0, .999): search_vqa.py:190-197) and the logsumexp-preserving rescale."""
+    MixedOp = mods['MixedOp']
+    h, b, nx, ny = 64, 2, 6, 4
+    torch.manual_seed(888)
+    m = MixedOp(op_cfg(h), 'dec_safe')
+    with torch.no_grad():
+        m.alpha_prob.copy_(torch.tensor([0.3, 1., -0.5, 0.5]))
+    opt = torch.optim.Adam([m.alpha_prob], 0.1, betas=(0., 0.999), weight_decay=0)
+    MixedOp.MODE = 'two'
+    torch.manual_seed(888)
+    m.binarize()
+    active, inactive = list(m.active_index), list(m.inactive_index)
+    x = torch.randn(b, nx, h, requires_grad=True)
+    y = torch.randn(b, ny, h, requires_grad=True)
+    rel = torch.relu(torch.randn(b, nx, nx, 64))
+    x_mask, y_mask = masks(b, nx, [6, 3]), masks(b, ny, [4, 1])
+    saved = {i: m.candidate_ops[i] for i in range(m.n_choices) if i not in active + inactive}
+    for i in saved:                                # Net_Search.unused_modules_off (hygr_vqa.py:175-187)
+        m.candidate_ops[i] = None
+    o = m(x, y, x_mask, y_mask, rel)
+    go = torch.randn_like(o)
+    o.backward(go)
+    for i, op in saved.items():
+        m.candidate_ops[i] = op
+    gate_grad = m.alpha_gate.grad.clone()
+    alpha_before = m.alpha_prob.detach().clone()
+    m.set_arch_param_grad()
+    prob_grad = m.alpha_prob.grad.clone()
+    opt.step()
+    alpha_adam = m.alpha_prob.detach().clone()
+    m.rescale_updated_arch_param()
+    rec = {'x': x, 'y': y, 'rel': rel, 'x_mask': x_mask, 'y_mask': y_mask, 'out': o, 'gout': go, 'gx': x.grad,
+           'gy': y.grad, 'active': np.array(active), 'inactive': np.array(inactive), 'gate_grad': gate_grad,
+           'prob_grad': prob_grad, 'alpha_before': alpha_before, 'alpha_adam': alpha_adam,
+           'alpha_rescaled': m.alpha_prob.detach().clone()}
+    for n_, p_ in m.named_parameters():
+        if 'alpha_prob' in n_:
+            rec['p.' + n_] = alpha_before
+        elif 'alpha_gate' in n_:
+            rec['p.' + n_] = p_
+        else:
+            rec['p.' + n_] = p_
+            if p_.grad is not None:
+                rec['g.' + n_] = p_.grad
+    MixedOp.MODE = None
+    np.savez_compressed(os.path.join(OUT, 'mixed_two_h64.npz'), **npify(rec))
+
+
+def golden_sampling(mods):
+    """The architecture samples the reference draws under its search seed: Net_Search.reset_binary_gates
+    (hygr_vqa.py:168-172 over MixedOp.binarize mixed.py:150-156) on the 12 + 18 node supernet with the init_arch prior
+    (hygr_vqa.py:142-156), torch.manual_seed(888) (search_vqa.py:62), CPU generator, five consecutive draws; plus the
+    draws after one alpha step moved the distribution."""
+    MixedOp = mods['MixedOp']
+    np.random.seed(888)
+    init = {'token_size': 30, 'ans_size': 11, 'pretrained_emb': np.zeros((30, 16), np.float32)}
+    cfg = net_cfg(64, nodes={'enc': 12, 'dec': 18})
+    torch.manual_seed(888)
+    net = mods['Net_Search'](cfg, init)
+    MixedOp.MODE = None
+    torch.manual_seed(888)
+    draws = []
+    for _ in range(5):
+        net.reset_binary_gates()
+        draws.append([m.active_index[0] for m in net.redundant_modules])
+    ga = torch.Generator().manual_seed(9)
+    alphas = []
+    for n_, p_ in net.named_alpha_prob_parameters():
+        p_.data = p_.data + 0.7 * torch.randn(p_.shape, generator=ga)
+        alphas.append(p_.detach().clone())
+    torch.manual_seed(889)
+    moved = []
+    for _ in range(3):
+        net.reset_binary_gates()
+        moved.append([m.active_index[0] for m in net.redundant_modules])
+    rec = {'draws_seed888': np.array(draws), 'draws_seed889_moved': np.array(moved)}
+    for i, a in enumerate(alphas):
+        rec['alpha%02d' % i] = a
+    np.savez_compressed(os.path.join(OUT, 'sampling_seed888.npz'), **npify(rec))
+
+
+def golden_losses():
+    """The ITM loss module of the reference (mmnas/utils/itm_loss.py BCE_Loss, REDUCTION 'sum') and the VGD loss
+    expression of train_vgd.py:252-256,320-334, evaluated literally with the torch.nn loss modules the script builds."""
+    from mmnas.utils.itm_loss import BCE_Loss
+    g = torch.Generator().manual_seed(11)
+    pos, negc, negi = (torch.rand(7, generator=g).requires_grad_(True) for _ in range(3))
+    loss = BCE_Loss(Bag(REDUCTION='sum'))(pos, negc, negi)
+    loss.backward()
+    rec = {'itm_pos': pos, 'itm_negc': negc, 'itm_negi': negi, 'itm_loss': loss, 'itm_gpos': pos.grad,
+           'itm_gnegc': negc.grad, 'itm_gnegi': negi.grad}
+    # --- VGD, the statements of train_vgd.py:252-256 and :320-334 with SCORES_LOSS='kld', LOSS_AVG=True, LOSS_LAMBDA=.5
+    b, n = 5, 9
+    pred_scores = torch.log_softmax(torch.randn(b, n, generator=g), -1).requires_grad_(True)
+    pred_reg = torch.randn(b, n, 4, generator=g).requires_grad_(True)
+    train_scores = torch.softmax(torch.randn(b, n, generator=g), -1) * (torch.rand(b, n, generator=g) > 0.5)
+    train_scores_mask = torch.tensor([[1.], [1.], [0.], [1.], [1.]])
+    train_transformed_bbox = torch.randn(b, n, 4, generator=g)
+    train_bbox_mask = (torch.rand(b, n, 1, generator=g) > 0.6).float()
+    scores_loss = torch.nn.KLDivLoss(reduction='sum')
+    reg_loss = torch.nn.SmoothL1Loss(reduction='sum')
+    loss_scores = scores_loss(pred_scores * train_scores_mask, train_scores * train_scores_mask)
+    loss_reg = reg_loss(pred_reg * train_bbox_mask, train_transformed_bbox * train_bbox_mask)
+    avg_scores = torch.sum(train_scores_mask.data)
+    avg_reg = torch.sum(train_bbox_mask.data)
+    loss_scores /= avg_scores
+    loss_reg /= avg_reg
+    loss = loss_scores + 0.5 * loss_reg
+    loss.backward()
+    rec.update({'vgd_pred_scores': pred_scores, 'vgd_pred_reg': pred_reg, 'vgd_scores': train_scores,
+                'vgd_scores_mask': train_scores_mask, 'vgd_tbox': train_transformed_bbox, 'vgd_bbox_mask': train_bbox_mask,
+                'vgd_loss': loss, 'vgd_gscores': pred_scores.grad, 'vgd_greg': pred_reg.grad})
+    np.savez_compressed(os.path.join(OUT, 'losses.npz'), **npify(rec))
+
+
 def golden_geometry():
     """relation_embedding (load_data_vqa.py:7-33).  The loader module needs spaCy, so only that
     function's source is extracted from the unmodified file and executed."""
@@ -259,13 +377,14 @@ def main():
     from mmnas.model.hygr_vqa import Net_Search
     mods = dict(MixedOp=MixedOp, OpsAdapter=OpsAdapter, Net_Full=Net_Full, Net_Search=Net_Search)
     torch.set_num_threads(1)
-    golden_ops(mods)
-    golden_mixed(mods)
-    golden_net_full(mods)
-    golden_net_search(mods)
-    golden_net_full_task('vgd')
-    golden_net_full_task('itm')
-    golden_geometry()
+    jobs = {'ops': lambda: golden_ops(mods), 'mixed': lambda: golden_mixed(mods), 'net_full': lambda: golden_net_full(mods),
+            'net_search': lambda: golden_net_search(mods), 'vgd': lambda: golden_net_full_task('vgd'),
+            'itm': lambda: golden_net_full_task('itm'), 'geometry': golden_geometry,
+            'mixed_two': lambda: golden_mixed_two(mods), 'sampling': lambda: golden_sampling(mods),
+            'losses': golden_losses}
+    only = [a for a in sys.argv[1:] if a in jobs] or list(jobs)      # `make_golden.py mixed_two sampling` regenerates two
+    for name in only:
+        jobs[name]()
     for f in sorted(os.listdir(OUT)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(OUT, f)))

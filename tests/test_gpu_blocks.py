@@ -117,8 +117,11 @@ def test_block_matches_oracle_at_baseline_shapes(name, mode, h, nx, ny, regime):
     for n_, p_ in op.named_parameters():
         # default-init RSA: geometry-path gradients are chaotic in float32 (condition_rsa_ docstring): logged only
         tol = None if (regime == 'default_init' and is_geometry_param(n_)) else GTOL[mode]
-        if tol is not None and n_.endswith('linear_r.bias'):
-            tol *= 10     # sum_j dS_ij = 0 per query row, so sum(dS / r) is a cancelling sum even when conditioned
+        if tol is not None and n_.endswith('linear_r.bias') and mode == 'fp32':
+            # sum_j dS_ij = 0 per query row, so sum(dS / r) is a cancelling sum even when conditioned: the fp32 arm
+            # (delta = dO.O from fp32 O) is held to 1e-4 instead of 2e-5; the bf16 arm forms delta in fp32 from the
+            # TMEM-resident P and dP (attention_tc.cu), cancels exactly and needs no allowance
+            tol = 1e-4
         pr.add(n_, p_.grad, P[n_].grad, tol, metric=gm)
     if name == 'rel_self_att_64':
         tol = None if regime == 'default_init' else GTOL[mode]
@@ -188,7 +191,8 @@ def test_mixed_op_full_mode_matches_reference_golden(mode):
     for n_, p_ in m.named_parameters():
         if n_.startswith('candidate_ops.%d.' % a):
             # linear_r.bias: cancelling sum (see test_block_matches_oracle_at_baseline_shapes)
-            pr.add(n_, p_.grad, r['g.' + n_], GTOL[mode] * (10 if n_.endswith('linear_r.bias') else 1), metric=gm)
+            pr.add(n_, p_.grad, r['g.' + n_], 1e-4 if (mode == 'fp32' and n_.endswith('linear_r.bias')) else GTOL[mode],
+                   metric=gm)
         elif n_.startswith('candidate_ops.'):
             assert p_.grad is None, n_
     pr.check()
@@ -215,3 +219,52 @@ def test_training_dropout_is_unbiased_and_replayable():
         mean = torch.stack(outs).mean(0)
     assert not torch.equal(outs[0], outs[1])
     assert normwise(mean, clean) < 0.08
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_mixed_op_two_mode_matches_reference_golden(mode):
+    """MODE 'two' (mixed.py:60-68 with the pair of :136-148): only the sampled pair runs, the inactive one detached;
+    alpha_gate.grad of both, the 2 x 2 alpha_prob rule, the alpha Adam step and the logsumexp rescale (:200-208)."""
+    import mmnas_b200
+    from mmnas_b200.model.mixed import MixedOp
+    r = load_golden('mixed_two_h64.npz')
+    m = MixedOp(Cfg(64), 'dec_safe')
+    m.load_state_dict(params_of(r))
+    m = m.to(DEV)
+    opt = torch.optim.Adam([m.alpha_prob], 0.1, betas=(0., 0.999), weight_decay=0)
+    m.active_index, m.inactive_index = r['active'].tolist(), r['inactive'].tolist()
+    involved = m.active_index + m.inactive_index
+    saved = {i: m.candidate_ops[i] for i in range(m.n_choices) if i not in involved}
+    MixedOp.MODE = 'two'
+    try:
+        for i in saved:
+            m.candidate_ops[i] = None             # Net_Search.unused_modules_off
+        x = r['x'].to(DEV).requires_grad_(True)
+        y = r['y'].to(DEV).requires_grad_(True)
+        with mmnas_b200.precision(mode):
+            out = m(x, y, r['x_mask'].to(DEV), r['y_mask'].to(DEV), r['rel'].to(DEV))
+            out.backward(r['gout'].to(DEV))
+        for i, op in saved.items():
+            m.candidate_ops[i] = op
+        gate_grad = m.alpha_gate.grad.clone()
+        m.set_arch_param_grad()
+        prob_grad = m.alpha_prob.grad.clone()
+        opt.step()
+        m.rescale_updated_arch_param()
+    finally:
+        MixedOp.MODE = None
+    pr = Parity('golden/mixed_two/%s' % mode)
+    gm = GMETRIC[mode]
+    pr.add('out', out, r['out'], TOL[mode])
+    pr.add('gx', x.grad, r['gx'], GTOL[mode], metric=gm)
+    pr.add('alpha_gate.grad', gate_grad, r['gate_grad'], GTOL[mode], metric=gm)
+    pr.add('alpha_prob.grad', prob_grad, r['prob_grad'], GTOL[mode], metric=gm)
+    pr.add('alpha_prob.rescaled', m.alpha_prob, r['alpha_rescaled'], 1e-4 if mode == 'fp32' else 2e-2)
+    a = involved[0]
+    for n_, p_ in m.named_parameters():
+        if n_.startswith('candidate_ops.%d.' % a):
+            pr.add(n_, p_.grad, r['g.' + n_], 1e-4 if (mode == 'fp32' and n_.endswith('linear_r.bias')) else GTOL[mode],
+                   metric=gm)
+        elif n_.startswith('candidate_ops.'):
+            assert p_.grad is None, n_
+    pr.check()

@@ -118,6 +118,16 @@ def test_net_full_vqa_at_baseline_config_matches_oracle(mode, regime):
     P = O.leaf_params(net.state_dict(), torch.float64)
     inp64 = tuple(t.double() if t.is_floating_point() else t for t in inputs)
     loss_ref, pred_ref = O.train_step_vqa(P, inp64, target.double(), cfg.GENOTYPE)
+    # the reference arithmetic's OWN float32 noise on the same tensors (float32 oracle vs float64 oracle, same CPU):
+    # the yardstick for the fp32 arm in the ill-conditioned default-init regime
+    own = {}
+    if mode == 'fp32' and regime == 'default_init':
+        P32 = O.leaf_params(net.state_dict(), torch.float32)
+        O.train_step_vqa(P32, inputs, target, cfg.GENOTYPE)
+        gmax = max(p.grad.abs().max().item() for p in P.values() if p.grad is not None)
+        for k, p32 in P32.items():
+            if p32.grad is not None and P[k].grad is not None:
+                own[k] = normwise(p32.grad, P[k].grad, 1e-2 * gmax)
     net = net.to(DEV)
     with mmnas_b200.precision(mode):
         pred = net(tuple(t.to(DEV) for t in inputs))
@@ -127,43 +137,67 @@ def test_net_full_vqa_at_baseline_config_matches_oracle(mode, regime):
     pr.add('pred', pred, pred_ref, TOL[mode])
     pr.add('loss', loss, loss_ref, TOL[mode])
     floor = 1e-2 * max(p.grad.abs().max().item() for p in P.values() if p.grad is not None)
+    if own:
+        worst = sorted(own.items(), key=lambda kv: -kv[1])[:3]
+        pr.rows.append(('reference fp32-vs-fp64, worst tensor: %s' % worst[0][0], worst[0][1], None))
     for n_, p_ in net.named_parameters():
         ref = P[n_].grad if P[n_].grad is not None else torch.zeros_like(P[n_])
-        # default init: the RSA geometry-path gradients are chaotic in float32 (tests/util.py condition_rsa_): logged
-        # only; the same near-clamp entries perturb dS and, through it, every gradient upstream of an RSA block,
-        # so the fp32 arm is held to 5e-3 here and to the strict 3e-5 in the conditioned regime.
         tol = GTOL[mode]
-        if regime == 'default_init':
-            tol = None if is_geometry_param(n_) else max(tol, 5e-3)
-        elif mode == 'fp32' and ('mlp.fc.linear' in n_ or n_.endswith('linear_r.bias')):
+        if mode == 'fp32' and ('mlp.fc.linear' in n_ or n_.endswith('linear_r.bias')):
             # a ReLU whose pre-activation is within float32 rounding of 0 takes the other branch than in the
             # float64 oracle (about one unit per FFN block at these sizes) and moves one token's contribution to
             # dW1 / db1; linear_r.bias is the cancelling sum described in test_gpu_blocks
             tol = 1e-3
+        if regime == 'default_init':
+            # The RSA geometry path is ill-conditioned in float32 at default init (tests/util.py condition_rsa_).
+            # fp32 arm: every tensor is held to 4x the error the reference arithmetic's OWN float32 evaluation shows
+            # on THAT tensor against float64 (8x for the four geometry-path gradients), never tighter than the strict
+            # gate.  bf16 arm: geometry gradients are logged only, the rest is held to the normal bf16 gate.
+            if mode == 'fp32':
+                tol = max(tol, (8.0 if is_geometry_param(n_) else 4.0) * own.get(n_, 0.0))
+            elif is_geometry_param(n_):
+                tol = None
         pr.add(n_, p_.grad, ref, tol, floor, metric=GMETRIC[mode])
     pr.check()
 
 
 def test_train_step_graph_replay_equals_eager():
-    """The captured CUDA graph of the whole step (fwd + bwd + clip + Adam) evolves the weights like eager steps."""
+    """The captured CUDA graph of the whole step (fwd + bwd + clip + Adam) evolves the model exactly like eager steps:
+    the warm-up steps that precede the capture are undone (engine.TrainStep._capture), so after k calls both runs have
+    applied k updates — same parameters, same Adam moments, same bias-correction count, same dropout step counter.
+    Dropout off: the two runs then differ only by the summation order of split-K / atomic accumulations."""
     import copy
     import mmnas_b200
+    from mmnas_b200 import runtime
     from mmnas_b200.engine import TrainStep
     from mmnas_b200.model.nets import Net_Full
     torch.manual_seed(1)
-    spec, cfg, init, inputs, target = full_setup(4)
+    spec, cfg, init, inputs, target = full_setup(4, p=0.0)
     net_a = Net_Full(cfg, init).to(DEV).train()
     net_b = copy.deepcopy(net_a)
     din, dt = tuple(t.to(DEV) for t in inputs), target.to(DEV)
     with mmnas_b200.precision('bf16'):
         eager = TrainStep(net_a, use_graph=False)
         graph = TrainStep(net_b, use_graph=True)
-        la = [eager(din, dt).item() for _ in range(6)]
-        lb = [graph(din, dt).item() for _ in range(6)]
-    # graph capture runs 3 warm-up + 1 capture step on the same batch before the first replay
-    assert lb[0] < la[0]
-    assert abs(lb[0] - la[4]) < 0.05 * abs(la[4])
-    assert la[5] < la[0]
+        rng0 = runtime.rng_state(DEV).clone()
+        la = [eager(din, dt).item() for _ in range(3)]
+        rng_eager = runtime.rng_state(DEV).clone()
+        runtime.rng_state(DEV).copy_(rng0)
+        lb = [graph(din, dt).item() for _ in range(3)]
+        rng_graph = runtime.rng_state(DEV).clone()
+    assert torch.equal(rng_eager, rng_graph)                       # dropout step counter: 3 advances in both runs
+    assert torch.equal(eager.optim.fused.state, graph.optim.fused.state) and int(graph.optim.fused.state[1]) == 3
+    for a, b in zip(la, lb):
+        assert abs(a - b) < 2e-3 * abs(a), (la, lb)                # same trajectory from the FIRST step on
+    assert la[2] < la[0]
+    pr = Parity('graph_vs_eager')
+    for (n_, pa), pb in zip(net_a.named_parameters(), net_b.parameters()):
+        pr.add(n_, pb, pa, 1e-3)
+    # Adam normalises by sqrt(v): where a gradient is ~0 the update direction is noise-dominated in both runs, so the
+    # moments are compared in the Frobenius norm
+    pr.add('exp_avg', graph.optim.fused.exp_avg, eager.optim.fused.exp_avg, 2e-2, metric='fro')
+    pr.add('exp_avg_sq', graph.optim.fused.exp_avg_sq, eager.optim.fused.exp_avg_sq, 2e-2, metric='fro')
+    pr.check()
 
 
 def test_search_step_weight_and_arch():
@@ -336,3 +370,182 @@ def test_eager_pytorch_port_timing_on_this_gpu_is_logged():
     os.makedirs('gpurun_out', exist_ok=True)
     json.dump({'workload': 'MMnas-VQA train step, B=64, dropout 0.1, eager PyTorch port (oracle) on cuda:0', **res},
               open('gpurun_out/eager_port_timing.json', 'w'), indent=1)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# round 2: backward parity of the VGD / ITM steps at H=512, SearchStep against the oracle at H=256 / B=64
+# ----------------------------------------------------------------------------------------------------------------
+def _grad_parity(pr, net, P, mode, skip_none=False):
+    gmax = max(p.grad.abs().max().item() for p in P.values() if p.grad is not None)
+    for n_, p_ in net.named_parameters():
+        if P[n_].grad is None:
+            if not skip_none and p_.grad is not None:
+                assert float(p_.grad.abs().max()) == 0.0, n_
+            continue
+        tol = GTOL[mode]
+        if mode == 'fp32' and ('mlp.fc.linear' in n_ or n_.endswith('linear_r.bias')):
+            tol = 1e-3      # ReLU-mask flips against float64 / cancelling sum (see the VQA test above)
+        pr.add(n_, p_.grad, P[n_].grad, tol, 1e-2 * gmax, metric=GMETRIC[mode])
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_vgd_train_step_backward_matches_oracle_at_baseline_shapes(mode):
+    """BASELINE config 4 (G): arch mmnas_vgd (5 RSA + 11 GA blocks), H=512, 100 valid regions, 15-token queries; the
+    step body of train_vgd.py:317-335 — KLD over masked log-softmax region scores + 0.5 SmoothL1 over masked box
+    regressions — forward AND every gradient against the float64 oracle (conditioned RSA regime)."""
+    import mmnas_b200
+    from mmnas_b200 import genotypes
+    from mmnas_b200.data.synthetic import Cfg, make_batch, init_dict, spec_for
+    from mmnas_b200.engine import vgd_loss
+    from mmnas_b200.model.nets import Net_Full
+    torch.manual_seed(888)
+    spec = spec_for('vgd', batch=4, vocab=1000, n_ans=10)
+    cfg = Cfg(genotype=genotypes.shipped('mmnas_vgd'), DROPOUT_R=0.0, SCORES_LOSS='kld')
+    inputs, target = make_batch(spec)
+    assert float(target[1].sum()) >= 2 and float(target[3].sum()) >= 2
+    net = Net_Full(cfg, init_dict(spec), task='vgd').train()
+    with torch.no_grad():
+        condition_rsa_(dict(net.named_parameters()))
+    P = O.leaf_params(net.state_dict(), torch.float64)
+    inp64 = tuple(t.double() if t.is_floating_point() else t for t in inputs)
+    loss_ref, (sc_ref, reg_ref) = O.train_step_vgd(P, inp64, tuple(t.double() for t in target), cfg.GENOTYPE)
+    net = net.to(DEV)
+    with mmnas_b200.precision(mode):
+        pred = net(tuple(t.to(DEV) for t in inputs))
+        loss = vgd_loss(pred, tuple(t.to(DEV) for t in target))
+        loss.backward()
+    pr = Parity('oracle/vgd_step_H512/%s' % mode)
+    pr.add('scores', pred[0], sc_ref, TOL[mode])
+    pr.add('reg', pred[1], reg_ref, TOL[mode])
+    pr.add('loss', loss, loss_ref, TOL[mode])
+    _grad_parity(pr, net, P, mode)
+    pr.check()
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_itm_train_step_backward_matches_oracle_at_baseline_shapes(mode):
+    """BASELINE config 5 (I): arch mmnas_itm, H=512, 36 regions, 50-token captions.  The reference runs THREE forwards
+    per step (positive, negative caption, negative image: train_itm.py:387-389) and BCE_Loss counts the positive term
+    twice (itm_loss.py:22).  Here the three forwards are one stacked batch; scores, loss and every gradient are
+    compared with the float64 oracle, which does run three separate forwards."""
+    import mmnas_b200
+    from mmnas_b200 import genotypes
+    from mmnas_b200.data.synthetic import Cfg, make_batch, init_dict, spec_for
+    from mmnas_b200.engine import itm_loss
+    from mmnas_b200.model.nets import Net_Full
+    torch.manual_seed(888)
+    B = 3
+    spec = spec_for('itm', batch=B, vocab=1000, n_ans=10)
+    cfg = Cfg(genotype=genotypes.shipped('mmnas_itm'), DROPOUT_R=0.0)
+    inputs, _ = make_batch(spec)
+    net = Net_Full(cfg, init_dict(spec), task='itm').train()
+    with torch.no_grad():
+        condition_rsa_(dict(net.named_parameters()))
+    P = O.leaf_params(net.state_dict(), torch.float64)
+    inp64 = tuple(t.double() if t.is_floating_point() else t for t in inputs)
+    thirds = [tuple(t[k * B:(k + 1) * B] for t in inp64) for k in range(3)]
+    loss_ref, scores_ref = O.train_step_itm(P, thirds[0], thirds[1], thirds[2], cfg.GENOTYPE)
+    net = net.to(DEV)
+    with mmnas_b200.precision(mode):
+        pred = net(tuple(t.to(DEV) for t in inputs))
+        loss = itm_loss(pred)
+        loss.backward()
+    pr = Parity('oracle/itm_step_H512/%s' % mode)
+    pr.add('scores', pred, torch.cat(scores_ref), TOL[mode])
+    pr.add('loss', loss, loss_ref, TOL[mode])
+    _grad_parity(pr, net, P, mode)
+    pr.check()
+
+
+def _search_setup(batch, p=0.0):
+    from mmnas_b200.data.synthetic import Cfg, SynthSpec, make_batch, init_dict
+    spec = SynthSpec(batch=batch, vocab=2000)
+    cfg = Cfg(mode='search', DROPOUT_R=p)
+    inputs, target = make_batch(spec, 888)
+    return spec, cfg, init_dict(spec), inputs, target
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_search_step_matches_oracle_at_baseline_config(mode):
+    """BASELINE config 3 (S): SearchStep at H=256, 4 heads, B=64 under the reference's search seed 888.
+    Weight step (search_vqa.py:278-300): the gradients of the sampled path.  Architecture step in MODE 'full'
+    (:305-332): alpha_gate.grad of all 30 nodes, alpha_prob.grad after set_arch_param_grad, the alphas after the
+    alpha Adam step and the genotype — all against the float64 oracle run on the path SearchStep sampled."""
+    import mmnas_b200
+    from mmnas_b200.engine import SearchStep
+    from mmnas_b200.model.nets import Net_Search
+    torch.manual_seed(888)
+    spec, cfg, init, inputs, target = _search_setup(64)
+    net = Net_Search(cfg, init).train()
+    with torch.no_grad():
+        condition_rsa_(dict(net.named_parameters()))
+    state0 = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net = net.to(DEV)
+    din, dt = tuple(t.to(DEV) for t in inputs), target.to(DEV)
+    inp64 = tuple(t.double() if t.is_floating_point() else t for t in inputs)
+
+    def oracle(state, mode_, choices):
+        P = O.leaf_params(state, torch.float64)
+        for kind, n in (('enc', 12), ('dec', 18)):
+            for i in range(n):
+                g = P['backnone.cells_%s.0.dag.%d.0.alpha_gate' % (kind, i)]
+                with torch.no_grad():
+                    g.zero_()
+                    g[choices[kind][i]] = 1.0
+        pred = O.net_search_vqa(P, inp64, mode_, choices)
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(pred, target.double(), reduction='sum')
+        loss.backward()
+        return P, pred.detach(), loss.detach()
+
+    with mmnas_b200.precision(mode):
+        step = SearchStep(net)
+        # ---- weight step on the sampled path
+        torch.manual_seed(888)
+        step.net.reset_binary_gates(batched=True)
+        picks = [m.active_index[0] for m in net.redundant_modules]
+        torch.manual_seed(888)                       # the step draws the same path again
+        loss_w = step.weight_step(din, dt)
+        assert [m.active_index[0] for m in net.redundant_modules] == picks
+        choices = {'enc': picks[:12], 'dec': picks[12:]}
+        Pw, _, loss_w_ref = oracle(state0, None, choices)
+        pr = Parity('oracle/search_weight_step_S_B64/%s' % mode)
+        pr.add('loss', loss_w, loss_w_ref, TOL[mode])
+        gmax = max(p.grad.abs().max().item() for p in Pw.values() if p.grad is not None)
+        for n_, p_ in net.named_net_parameters():
+            ref = Pw[n_].grad
+            if ref is None:                          # unsampled candidates: zero gradient (the dummy-loss terms)
+                assert float(p_.grad.abs().max()) == 0.0, n_
+                continue
+            tol = GTOL[mode]
+            if mode == 'fp32' and ('mlp.fc.linear' in n_ or n_.endswith('linear_r.bias')):
+                tol = 1e-3
+            pr.add(n_, p_.grad, ref, tol, 1e-2 * gmax, metric=GMETRIC[mode])
+        pr.check()
+        # ---- architecture step, from the weights the weight step produced
+        state1 = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+        alphas1 = {n_: p_.detach().cpu().clone() for n_, p_ in net.named_alpha_prob_parameters()}
+        loss_a = step.arch_step(din, dt)
+        picks_a = [m.active_index[0] for m in net.redundant_modules]
+        choices_a = {'enc': picks_a[:12], 'dec': picks_a[12:]}
+        Pa, _, loss_a_ref = oracle(state1, 'full', choices_a)
+    pr = Parity('oracle/search_arch_step_S_B64/%s' % mode)
+    pr.add('loss', loss_a, loss_a_ref, TOL[mode])
+    gate_ref = {k: v.grad for k, v in Pa.items() if k.endswith('alpha_gate')}
+    gfloor = 1e-2 * max(g.abs().max().item() for g in gate_ref.values())
+    ref_alphas = []
+    for (n_, p_), (ng, pg) in zip(net.named_alpha_prob_parameters(), net.named_alpha_gate_parameters()):
+        g_ref = gate_ref[ng]
+        pr.add(ng + '.grad', pg.grad, g_ref, 5 * GTOL[mode], gfloor, metric=GMETRIC[mode])       # cancelling sums
+        prob_ref = O.arch_param_grad(alphas1[n_].double(), g_ref)
+        pr.add(n_ + '.grad', p_.grad, prob_ref, 5 * GTOL[mode], gfloor, metric=GMETRIC[mode])
+        a = alphas1[n_].double().clone().requires_grad_(True)       # alpha Adam, lr 0.1, betas (0, .999): first step
+        a.grad = prob_ref
+        torch.optim.Adam([a], 0.1, betas=(0., 0.999), weight_decay=0).step()
+        ref_alphas.append(a.detach())
+        # sign-of-gradient step: entries whose gradient is ~0 relative to the node's scale may land on either side
+        big = prob_ref.abs() > 0.05 * prob_ref.abs().max()
+        assert torch.allclose(p_.detach().cpu().double()[big], a.detach()[big], atol=2e-3 if mode == 'fp32' else 2e-2), n_
+    pr.check()
+    geno_ref = {'enc': [[O.ENC_SAFE[int(a.argmax())]] for a in ref_alphas[:12]],
+                'dec': [[O.DEC_SAFE[int(a.argmax())]] for a in ref_alphas[12:]]}
+    assert net.genotype() == geno_ref                # identical argmax-selected architecture, both arms

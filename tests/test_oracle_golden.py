@@ -136,3 +136,40 @@ def test_net_full_vgd_itm_match_golden(task):
     for k, p in P.items():
         g = p.grad if p.grad is not None else torch.zeros_like(p)
         assert normwise(g, r['g.' + k], floor) < 5e-6, k
+
+
+def test_mixed_two_mode_matches_golden():
+    """MODE 'two' (mixed.py:136-148, :179-191, :200-208): pair sampling, gated output, 2 x 2 gradient rule, rescale."""
+    r = load_golden('mixed_two_h64.npz')
+    P = O.leaf_params(params_of(r))
+    torch.manual_seed(888)
+    active, inactive = O.binarize_two(P['alpha_prob'])
+    assert [active] == r['active'].tolist() and [inactive] == r['inactive'].tolist()
+    x, y = (r[k].clone().requires_grad_(True) for k in ('x', 'y'))
+    out = O.mixed_forward(O.DEC_SAFE, P, '', x, y, r['x_mask'], r['y_mask'], r['rel'], 'two', [active], [inactive])
+    assert normwise(out, r['out']) < TOL
+    out.backward(r['gout'])
+    assert normwise(x.grad, r['gx']) < TOL
+    assert normwise(P['alpha_gate'].grad, r['gate_grad']) < TOL
+    g = O.arch_param_grad_two(P['alpha_prob'], P['alpha_gate'].grad, active, inactive)
+    assert normwise(g, r['prob_grad']) < TOL
+    assert normwise(O.rescale_two(r['alpha_adam'], r['alpha_before'], active, inactive), r['alpha_rescaled']) < TOL
+    untouched = [i for i in range(4) if i not in (active, inactive)]
+    assert torch.equal(r['alpha_rescaled'][untouched], r['alpha_before'][untouched])
+
+
+def test_losses_match_golden():
+    """BCE_Loss of mmnas/utils/itm_loss.py (positive term twice) and the VGD loss of train_vgd.py:320-334."""
+    r = load_golden('losses.npz')
+    pos, negc, negi = (r[k].clone().requires_grad_(True) for k in ('itm_pos', 'itm_negc', 'itm_negi'))
+    loss = O.itm_bce_loss(pos, negc, negi)
+    loss.backward()
+    assert normwise(loss, r['itm_loss']) < TOL
+    for t, k in ((pos, 'itm_gpos'), (negc, 'itm_gnegc'), (negi, 'itm_gnegi')):
+        assert normwise(t.grad, r[k]) < TOL
+    assert normwise(pos.grad, 2 * (-1 / r['itm_pos'])) < TOL          # the double-counted positive term
+    ps, pr = (r[k].clone().requires_grad_(True) for k in ('vgd_pred_scores', 'vgd_pred_reg'))
+    loss = O.vgd_loss(ps, pr, r['vgd_scores'], r['vgd_scores_mask'], r['vgd_tbox'], r['vgd_bbox_mask'])
+    loss.backward()
+    assert normwise(loss, r['vgd_loss']) < TOL
+    assert normwise(ps.grad, r['vgd_gscores']) < TOL and normwise(pr.grad, r['vgd_greg']) < TOL
