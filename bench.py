@@ -1,12 +1,15 @@
 """bench.py — MMnas-VQA train throughput on B200 (BASELINE.json configs[1]).
 
     python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun, one rank per GPU)
-    python bench.py --impl reference ...                      the reference's CPU path (oracle port) on host cores
+    python bench.py --impl reference ...                      the reference's own modules (baseline/_ref) on host cores
 
 A step = one pass of the hot path over one synthetic batch: the train step of train_vqa.py:294-311 (forward of
 Net_Full with arch mmnas_vqa — 12 encoder + 18 decoder blocks through the CUDA operators —, BCE-sum loss,
 backward, gradient mean over ranks, clip_grad_norm_ 1.0, Adam) at B=64 per GPU, dropout 0.1, bf16 arm.
-Prints ONE JSON line (rank 0).
+`value` / `e2e` / `roofline` describe that workload (BASELINE configs[1]).  The same JSON line carries a `workloads`
+object with the other BASELINE configs measured at the run's N through the same engine: the supernet search step
+(configs[2]: weight step, architecture step, the 4:1 mix of ALPHA_EVERY=5), the VGD step (configs[3]) and the ITM step
+(configs[4]).  Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
@@ -35,6 +38,8 @@ def parse():
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-workloads', action='store_true', help='skip the search / VGD / ITM workloads')
+    ap.add_argument('--workload-steps', type=int, default=20)
     ap.add_argument('--profile-out', default=None, help='write the live per-kernel table (JSON) here')
     return ap.parse_args()
 
@@ -48,19 +53,50 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------ CPU reference arm
+REF_DIR = os.path.join(ROOT, 'baseline', '_ref')
+
+
+def reference_available():
+    return os.path.exists(os.path.join(REF_DIR, 'mmnas', 'model', 'full_vqa.py'))
+
+
 def cpu_step_fn(batch, threads=None):
-    """The oracle port of the reference's train step (oracle/mmnas_oracle.py) on the host cores."""
+    """The reference's train step on the host cores.  With baseline/_ref present (the byte-identical copy of the
+    reference's model package, scripts/install_reference.py) this is the UNMODIFIED reference: its full_vqa.Net_Full,
+    its operators, its WarmupOptimizer, driven by the step body of train_vqa.py:294-311 — kind 'reference'.  Without
+    it, the oracle port (oracle/mmnas_oracle.py) — kind 'port'."""
     import torch
-    from oracle import mmnas_oracle as O
     from mmnas_b200 import genotypes
     from mmnas_b200.data.synthetic import Cfg, SynthSpec, make_batch, init_dict
-    from mmnas_b200.model.nets import Net_Full
     if threads:
         torch.set_num_threads(threads)
     torch.manual_seed(888)
     spec = SynthSpec(batch=batch)
     cfg = Cfg(genotype=genotypes.shipped('mmnas_vqa'))
     inputs, target = make_batch(spec)
+    if reference_available():
+        sys.path.insert(1, REF_DIR)
+        from mmnas.model.full_vqa import Net_Full          # the reference's own net, operators and optimizer wrapper
+        from mmnas.utils.optimizer import WarmupOptimizer
+        import mmnas.model.modules as ref_modules
+        assert ref_modules.__file__.startswith(REF_DIR), 'reference arm must run the reference operators'
+        net = Net_Full(cfg, init_dict(spec)).train()
+        optim = WarmupOptimizer(cfg.NET_LR_BASE, torch.optim.Adam(net.parameters(), lr=0, betas=cfg.OPT_BETAS,
+                                                                  eps=cfg.OPT_EPS, weight_decay=0), 10 ** 6, warmup=True)
+        loss_fn = torch.nn.BCEWithLogitsLoss(reduction='sum')
+
+        def step():                                        # train_vqa.py:294-311
+            optim.zero_grad()
+            pred = net(inputs)
+            loss = loss_fn(pred, target)
+            loss += 0 * sum(p.sum() for p in net.parameters())
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(net.parameters(), cfg.NET_GRAD_CLIP)
+            optim.step()
+            return float(loss)
+        return step, 'reference'
+    from oracle import mmnas_oracle as O
+    from mmnas_b200.model.nets import Net_Full
     net = Net_Full(cfg, init_dict(spec))          # parameter container only; the arithmetic below is the oracle's
     P = O.leaf_params(net.state_dict(), torch.float32)
     params = [p for p in P.values() if p.requires_grad]
@@ -74,22 +110,23 @@ def cpu_step_fn(batch, threads=None):
         loss, _ = O.train_step_vqa(P, inputs, target, cfg.GENOTYPE, p=cfg.DROPOUT_R, training=True)
         O.clip_and_adam(params, state, counter[0], lr=cfg.NET_LR_BASE / 4, max_norm=1.0)
         return float(loss)
-    return step
+    return step, 'port'
 
 
 def cpu_baseline(seconds=12.0, batch=BATCH):
     import torch
     cores = os.cpu_count() or 1
-    step = cpu_step_fn(batch, cores)
+    step, kind = cpu_step_fn(batch, cores)
     step()                                         # warm-up
     t0, n = time.perf_counter(), 0
-    while n < 1 or (time.perf_counter() - t0 < seconds and n < 3):
+    while n < 1 or (time.perf_counter() - t0 < seconds and n < 5):
         step()
         n += 1
     dt = (time.perf_counter() - t0) / n
-    return {'value': batch / dt, 'unit': 'samples/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-            'sample': '%d train steps of the oracle port (torch CPU fp32) at batch %d, %.2f s/step, after 1 warm-up'
-                      % (n, batch, dt)}
+    what = ('the unmodified reference (full_vqa.Net_Full + WarmupOptimizer from baseline/_ref)' if kind == 'reference'
+            else 'the oracle port')
+    return {'value': batch / dt, 'unit': 'samples/s', 'cores': torch.get_num_threads(), 'kind': kind,
+            'sample': '%d train steps of %s, torch CPU fp32, batch %d, %.2f s/step, after 1 warm-up' % (n, what, batch, dt)}
 
 
 def run_reference(args):
@@ -97,9 +134,8 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
-    total = args.steps + args.warmup
-    batch = BATCH if total <= 12 else (16 if total <= 40 else 8)
-    step = cpu_step_fn(batch, os.cpu_count())
+    batch = BATCH                                  # the full configs[1] batch: same config as the B200 arm
+    step, kind = cpu_step_fn(batch, os.cpu_count())
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -110,11 +146,12 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'samples/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'sample_batch': batch,
-                       'note': 'reference CPU path = oracle port of the reference train step (the reference itself '
-                               'is Python and cannot travel to the GPU box); each step is a bounded sample of '
-                               '%d of the 64 samples' % batch},
-            'cpu_baseline': {'value': val, 'unit': 'samples/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+            'config': {'workload': WORKLOAD, 'global_batch': batch,
+                       'note': ('reference CPU path: the UNMODIFIED reference modules (baseline/_ref: full_vqa.Net_Full, '
+                                'modules.py operators, WarmupOptimizer) through the step body of train_vqa.py:294-311, '
+                                'all host cores, batch 64' if kind == 'reference' else
+                                'reference CPU path = oracle port (baseline/_ref not present)')},
+            'cpu_baseline': {'value': val, 'unit': 'samples/s', 'cores': torch.get_num_threads(), 'kind': kind,
                              'sample': '%d steps at batch %d' % (args.steps, batch)},
             'e2e': {'value': val, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
@@ -191,10 +228,11 @@ def kernel_table(records):
         elif name in ('mmnas_ln_residual_fwd', 'mmnas_ln_residual_bwd'):
             byts = 4.0 * a[0] * a[1] * 3
         elif name in ('mmnas_relbias_fwd', 'mmnas_relbias_bwd'):
-            B, N, h = a[0], a[1], a[2]
+            B, N, h = a[1], a[2], a[3]             # (mode, B, N, heads, R, rel, g4, ...)
             pairs = float(B) * N * N
-            flops = pairs * 2 * (64 * 4 + 64 * h) * (1 if name.endswith('fwd') else 3)
-            byts = pairs * (16 + 4 * h) if a[5] else pairs * (256 + 4 * h)
+            geometry = a[6] is not None            # g4 given: the 4 -> 64 layer is recomputed in the kernel
+            flops = pairs * 2 * ((64 * 4 if geometry else 0) + 64 * h) * (1 if name.endswith('fwd') else 3)
+            byts = pairs * ((16 if geometry else 256) + 4 * h) * (1 if name.endswith('fwd') else 2)
         elif name == 'mmnas_cast_f32_to_bf16':
             byts = 6.0 * a[2]
         elif name == 'mmnas_colsum':
@@ -202,6 +240,91 @@ def kernel_table(records):
         f = fam.setdefault(key, {'launches': 0, 'ms': 0.0, 'flops': 0.0, 'bytes': 0.0})
         f['launches'] += 1; f['ms'] += ms; f['flops'] += flops; f['bytes'] += byts
     return fam
+
+
+def run_workloads(args, world, rank, dev, barrier):
+    """BASELINE configs[2..4] at the run's N: device-resident synthetic batches (as `value`), CUDA events, max over
+    ranks, B=64 per GPU, bf16 arm, dropout 0.1, data-parallel gradient mean where N > 1."""
+    import torch
+    import torch.distributed as dist
+    import mmnas_b200
+    from mmnas_b200 import _lib, genotypes
+    from mmnas_b200.data.synthetic import Cfg, make_batch, init_dict, spec_for
+    from mmnas_b200.engine import TrainStep, SearchStep, LOSSES, tree_map
+    from mmnas_b200.model.nets import Net_Full, Net_Search
+    steps = max(3, min(args.steps, args.workload_steps))
+
+    def timed(fn, n):
+        for _ in range(3):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.LAUNCHES
+        e0.record()
+        for _ in range(n):
+            out = fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / n, float(out), (_lib.LAUNCHES - l0) // n
+
+    def to_dev(batch):
+        return tree_map(lambda t: t.to(dev), batch)
+
+    out = {}
+    # ---- configs[2]: supernet search step (search_vqa.py:278-337), H=256, 4 heads, 12 + 18 MixedOp nodes
+    torch.manual_seed(888)
+    spec = spec_for('vqa', batch=BATCH)
+    cfg = Cfg(mode='search')
+    net = Net_Search(cfg, init_dict(spec)).to(dev).train()
+    mmnas_b200.manual_seed(888 + rank, dev)
+    train_b, eval_b = to_dev(make_batch(spec, seed=2000 + 17 * rank)), to_dev(make_batch(spec, seed=3000 + 17 * rank))
+    sstep = SearchStep(net, lr_base=cfg.NET_LR_BASE, epoch_steps=10 ** 6, alpha_lr=cfg.ALPHA_LR_BASE,
+                       alpha_betas=cfg.ALPHA_OPT_BETAS, mode=cfg.ALPHA_BINARY_MODE)
+    tw, lw, nw = timed(lambda: sstep.weight_step(*train_b), steps)
+    ta, la, na = timed(lambda: sstep.arch_step(*eval_b), steps)
+    every = cfg.ALPHA_EVERY
+    out['search_vqa'] = {
+        'config': 'BASELINE configs[2]: MMnas-VQA supernet search step, H=256, 4 heads, MixedOp over SA/FFN (12 enc nodes) '
+                  'and SA/RSA/GA/FFN (18 dec nodes), batch 64 per GPU, dropout 0.1, eager launches (the sampled path '
+                  'changes every step), seed-888 sampling with the reference\'s RNG consumption',
+        'weight_step': {'ms_per_step': tw, 'samples_per_s': BATCH * world / (tw / 1e3), 'launches_per_step': nw,
+                        'final_loss': lw},
+        'arch_step': {'ms_per_step': ta, 'samples_per_s': BATCH * world / (ta / 1e3), 'launches_per_step': na,
+                      'final_loss': la, 'mode': cfg.ALPHA_BINARY_MODE},
+        'mix': {'samples_per_s': every * BATCH * world / ((every * tw + ta) / 1e3), 'unit': 'train samples/s',
+                'how': 'ALPHA_EVERY=%d (search_vqa.py:150,305): %d weight steps + 1 architecture step per %d iterations'
+                       % (every, every, every)},
+        'steps': steps}
+    del sstep, net, train_b, eval_b
+    torch.cuda.empty_cache()
+
+    # ---- configs[3] / configs[4]: VGD and ITM train steps (train_vgd.py:317-341, train_itm.py:384-397)
+    for task, arch, lr, label in (
+            ('vgd', 'mmnas_vgd', 0.00014, 'BASELINE configs[3]: MMnas-VGD train step, arch mmnas_vgd (RSA-heavy: 5 RSA + 11 GA '
+             'blocks), H=512, 100 valid regions + boxes, 15-token queries, KLD + 0.5 SmoothL1 loss, batch 64 per GPU'),
+            ('itm', 'mmnas_itm', 0.00015, 'BASELINE configs[4]: MMnas-ITM train step, arch mmnas_itm, H=512, 36 regions, 50-token '
+             'captions, batch 64 per GPU = 64 positive pairs + 64 negative-caption + 64 negative-image pairs: the '
+             'reference\'s three forwards per step run as one stacked batch of 192 pairs; BCE_Loss (positive term twice)')):
+        torch.manual_seed(888)
+        spec = spec_for(task, batch=BATCH)
+        cfg = Cfg(genotype=genotypes.shipped(arch), SCORES_LOSS='kld')
+        net = Net_Full(cfg, init_dict(spec), task=task).to(dev).train()
+        mmnas_b200.manual_seed(888 + rank, dev)
+        inputs, target = to_dev(make_batch(spec, seed=4000 + 17 * rank))
+        use_graph = not args.no_graph and (world == 1 or os.environ.get('MMNAS_DP_GRAPH', '1') == '1')
+        tstep = TrainStep(net, lr_base=lr, epoch_steps=10 ** 6, use_graph=use_graph, loss_fn=LOSSES[task])
+        ms, loss, _ = timed(lambda: tstep(inputs, target), steps)
+        out['train_' + task] = {'config': label, 'ms_per_step': ms, 'samples_per_s': BATCH * world / (ms / 1e3),
+                                'pairs_forwarded_per_s': (3 if task == 'itm' else 1) * BATCH * world / (ms / 1e3),
+                                'final_loss': loss, 'cuda_graph': use_graph, 'steps': steps}
+        del tstep, net, inputs, target
+        torch.cuda.empty_cache()
+    out['note'] = ('same engine, timing rule and per-GPU batch as `value`; n_gpus = %d, gradient mean over ranks '
+                   'inside every step when n_gpus > 1' % world)
+    return out
 
 
 # ------------------------------------------------------------------------------------------ B200 arm
@@ -220,8 +343,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'INFO', 'TRACE'):
-            os.environ['NCCL_DEBUG'] = 'WARN'     # keep stdout to the single JSON line
+        # NCCL_DEBUG is left as the caller set it: main() re-routed fd 1 to stderr, so NCCL's INFO lines cannot mix
+        # with the single JSON line on stdout
         dist.init_process_group('nccl', device_id=dev)
     mmnas_b200.set_precision(args.precision)
     _lib.load()
@@ -321,7 +444,7 @@ def run_b200(args):
     except (OSError, ValueError, KeyError):
         pass
     roofline = {'kernel': top_name, 'bound': bound, 'achieved': ach, 'peak': peak, 'unit': unit, 'frac': ach / peak,
-                'traffic': traffic, 'peak_source': pk['src'] + (' (sustained)' if bound == 'tensor' else ''),
+                'traffic': traffic, 'traffic_source': 'static: profiles/ncu_traffic.json (one ncu --set full capture of this kernel family; dram bytes per launch), not measured in this run', 'peak_source': pk['src'] + (' (sustained)' if bound == 'tensor' else ''),
                 'avg_launch_ms': top['ms'] / top['launches'], 'launches_per_step': top['launches'] // n_prof,
                 'algorithmic_per_launch': (top['flops'] if bound == 'tensor' else top['bytes']) / top['launches'],
                 'share_of_kernel_time': top['ms'] / tot_ms,
@@ -334,6 +457,13 @@ def run_b200(args):
                 for k, v in fam.items()}
         json.dump({'kernels': rows, 'kernel_ms_per_step': tot_ms / n_prof, 'step_ms': ms_step}, open(args.profile_out, 'w'),
                   indent=1)
+
+    # ---- the other BASELINE configs at this N, through the same engine (`workloads`)
+    workloads = None
+    if not args.no_workloads:
+        del step, prof_step, pre
+        torch.cuda.empty_cache()
+        workloads = run_workloads(args, world, rank, dev, barrier)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -354,6 +484,8 @@ def run_b200(args):
                                      (launches_per_step, 'replayed from the captured CUDA graph in the timed region'
                                       if use_graph else 'launched eagerly'),
                 'roofline': roofline}
+        if workloads:
+            line['workloads'] = workloads
         if cpu:
             line['cpu_baseline'] = cpu
         emit(line)

@@ -137,10 +137,17 @@ def stream():
 
 
 def require_cuda(*tensors):
+    """CUDA tensors only, and on the CURRENT device: the launch stream is resolved from the current device, so a
+    tensor of another GPU would be launched on the wrong device / stream."""
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise MMnasLibraryError('mmnas_b200 operators run on CUDA tensors only (got a %s tensor); '
                                     'there is no CPU path.' % t.device)
+        if _raw_device is not None and t.device.index != _raw_device():
+            raise MMnasLibraryError('tensor lives on cuda:%d but the current device is cuda:%d: wrap the call in '
+                                    'torch.cuda.device(tensor.device)' % (t.device.index, _raw_device()))
 
 
 def ptr_array(tensors):

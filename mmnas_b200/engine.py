@@ -173,8 +173,21 @@ class WeightShadows:
                     off += n
         self.n_chunks = len(rows)
         self.table = torch.tensor(rows, dtype=torch.int64, device=self.buffers[0].device) if rows else None
+        self._watch = [(p, p.data_ptr()) for p in self._watched(net)]
+
+    @staticmethod
+    def _watched(net):
+        ps = [p for mod in net.modules() if hasattr(mod, 'shadow_specs') for _, _, params in mod.shadow_specs()
+              for p in params if p.is_cuda]
+        return ps[:1] + ps[-1:]
 
     def refresh(self):
+        # the device table holds raw parameter addresses: a storage change (net.to(), p.data = ...) would make the
+        # kernel read stale memory without any error, so the first and last entries are re-checked on every call
+        for p, ptr in self._watch:
+            if p.data_ptr() != ptr:
+                raise RuntimeError('parameter storage moved after the engine step was built (net.to() / p.data = ...): '
+                                   're-create the TrainStep / SearchStep')
         if self.n_chunks:
             self.kernels.cast_multi(self.table, self.n_chunks)
 
@@ -211,6 +224,16 @@ class WarmupAdam:
 
     def decay(self, r):
         self.lr_base *= r
+
+    def set_start_step(self, step):
+        """optimizer.py:48-49 (resume): the schedule continues from `step`."""
+        self._step = step
+
+    def state_dict(self):
+        return self.fused.state_dict() if self.fused is not None else self.optimizer.state_dict()
+
+    def load_state_dict(self, sd):
+        (self.fused if self.fused is not None else self.optimizer).load_state_dict(sd)
 
     def set_lr(self):
         """Host side of a step: advance the schedule and publish the learning rate."""
@@ -270,8 +293,45 @@ class FusedClipAdam:
             assert p.is_contiguous()
         self.n_chunks = len(rows)
         self.table = torch.tensor(rows, dtype=torch.int64, device=dev)
+        self.params = [fg.params[i] for i in idx]
+        self.offsets = [fg.offsets[i] - self.lo for i in idx]
+        self._watch = [(fg.params[i], fg.params[i].data_ptr(), fg.views[i].data_ptr(), i) for i in (first, last)]
+        self._fg = fg
+
+    def _check_storage(self):
+        for p, ptr, gptr, i in self._watch:
+            if p.data_ptr() != ptr or self._fg.views[i].data_ptr() != gptr:
+                raise RuntimeError('parameter / gradient storage moved after the optimizer was built (net.to(), '
+                                   'p.data = ..., a new FlatGrads): re-create the TrainStep / SearchStep')
+
+    # torch.optim.Adam's state layout, so that the reference checkpoint entry 'net_optim' (train_vqa.py:315-321) can be
+    # produced and resumed: {'state': {i: {'step', 'exp_avg', 'exp_avg_sq'}}, 'param_groups': [...]}
+    def state_dict(self):
+        step = float(self.state[1].item())
+        st = {}
+        for i, (p, off) in enumerate(zip(self.params, self.offsets)):
+            n = p.numel()
+            st[i] = {'step': torch.tensor(step), 'exp_avg': self.exp_avg[off:off + n].view_as(p).clone(),
+                     'exp_avg_sq': self.exp_avg_sq[off:off + n].view_as(p).clone()}
+        return {'state': st, 'param_groups': [{'lr': float(self.lr.item()), 'betas': tuple(self.betas), 'eps': self.eps,
+                                               'weight_decay': 0, 'amsgrad': False,
+                                               'params': list(range(len(self.params)))}]}
+
+    def load_state_dict(self, sd):
+        step = 0
+        with torch.no_grad():
+            for i, (p, off) in enumerate(zip(self.params, self.offsets)):
+                ent = sd['state'].get(i)
+                if ent is None:
+                    continue
+                n = p.numel()
+                self.exp_avg[off:off + n].copy_(ent['exp_avg'].reshape(-1))
+                self.exp_avg_sq[off:off + n].copy_(ent['exp_avg_sq'].reshape(-1))
+                step = max(step, int(float(ent['step'])))
+            self.state[1] = step
 
     def step(self):
+        self._check_storage()
         k = self.kernels
         k.rng_advance(self.state)
         if self.clip > 0:

@@ -37,7 +37,7 @@ def main():
     import mmnas.model.modules as M
     from mmnas_b200.data.synthetic import Cfg, SynthSpec, make_batch, init_dict
     from tests.util import condition_rsa_
-    dev = 'cuda:0'
+    dev = os.environ.get('MMNAS_DROPIN_DEV', 'cuda:0')      # ('cpu' only to smoke-test the reference leg without a GPU)
     res = {'modules': M.__name__}
 
     # ---- 1. train-time net from the reference's arch JSON

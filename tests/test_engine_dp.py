@@ -131,3 +131,46 @@ def test_flat_grads_survive_grad_none_and_warmup_schedule():
     assert rates == [0.25, 0.25, 0.5, 0.5, 0.75, 0.75, 1.0, 1.0]      # optimizer.py:25-44
     opt.decay(0.2)
     assert abs(opt.rate(1000) - 0.2) < 1e-12
+
+
+def _sampling_worker(rank, world, port, q):
+    """Ranks with DIFFERENT torch seeds must still run the same supernet path: the step harness broadcasts rank 0's
+    picks (the reference only relies on identically seeded ranks, search_vqa.py:62-66)."""
+    import numpy as np
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from mmnas_b200.data.synthetic import Cfg
+        from mmnas_b200.model.nets import Net_Search
+        cfg = Cfg(mode='search', HSIZE=64, FRCNFEAT_SIZE=32, BBOXFEAT_EMB_SIZE=32, WORD_EMBED_SIZE=16, ATTFLAT_MLP_SIZE=48,
+                  ATTFLAT_OUT_SIZE=128)
+        torch.manual_seed(888)
+        net = Net_Search(cfg, {'token_size': 30, 'ans_size': 11, 'pretrained_emb': np.zeros((30, 16), np.float32)})
+        torch.manual_seed(888 + 1000 * rank)               # ranks drift apart on purpose
+        draws = []
+        for _ in range(3):
+            net.reset_binary_gates(batched=True)
+            draws.append([m.active_index[0] for m in net.redundant_modules])
+            for m in net.redundant_modules:
+                assert float(m.alpha_gate.data[m.active_index[0]]) == 1.0 and float(m.alpha_gate.data.sum()) == 1.0
+        q.put((rank, draws))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_search_sampling_is_rank_invariant_under_data_parallelism():
+    world, port = 2, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sampling_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=100) for _ in range(world))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    assert got[0] == got[1]
+    from tests.util import load_golden
+    assert got[0] == load_golden('sampling_seed888.npz')['draws_seed888'].tolist()[:3]     # rank 0 draws the seed-888 path
