@@ -23,12 +23,14 @@
 extern "C" {
 #endif
 
-#define MMNAS_B200_ABI_VERSION 6
+#define MMNAS_B200_ABI_VERSION 7
 
 typedef void* mmnas_stream;
 
 int mmnas_abi_version(void);
 const char* mmnas_last_error(void);
+/* number of CUDA kernels this library has launched in this process so far (memsets not counted) */
+unsigned long long mmnas_launch_count(void);
 
 /* ---- dense contractions: nn.Linear forward/backward (modules.py:18,38,172-175,216-220) ----------------
  * fp32 arm (FFMA): C[M,N] = epi(A @ B (+bias[N])) (+C);  A(m,k) = A[m*a_rs + k*a_cs], B(k,n) = B[k*b_rs + n*b_cs].
@@ -67,7 +69,7 @@ int mmnas_attn_bwd(int dtype, int B, int heads, int Nq, int Nk, int head_dim, co
  * Exactly one of rel [B,N,N,R] (the reference's dense tensor) or g4 [B,N,N,4] (+Wy [R,4], by [R]: the
  * relu(linear_y_rel(.)) of full_vqa.py:103 folded in) is non-NULL.  bias out: [B,heads,N,N].  R == 64, heads <= 16.
  * mode 0: fp32 arithmetic (parity arm).  mode 1 (bf16 arm): the 64-channel contractions run on the tensor cores with
- * split-bf16 operands for r and plain bf16 operands for the gradient products (geometry input, 8 heads; any other
+ * split-bf16 operands for r and plain bf16 operands for the gradient products (geometry input, 2-8 heads; any other
  * configuration silently uses the mode-0 kernels). */
 int mmnas_relbias_fwd(int mode, int B, int N, int heads, int R, const float* rel, const float* g4, const float* Wy,
                       const float* by, const float* Wr, const float* br, float* bias, mmnas_stream stream);
@@ -123,6 +125,100 @@ int mmnas_clip_adam(const void* table, int n_chunks, const float* sumsq, const f
                     mmnas_stream stream);
 /* state[1] += 1: call once per training step so every step draws fresh dropout masks (graph-capturable). */
 int mmnas_rng_advance(unsigned long long* state, mmnas_stream stream);
+
+/* =========================================================================================================
+ * Block-level entry points (ABI v7): ONE call enqueues the whole kernel sequence of a candidate block, forward or
+ * backward, including the side-stream fork / join of the weight-gradient GEMMs.  They replace the forward/backward of
+ *   SelfAtt.forward      modules.py:260-271     GuidedAtt.forward    modules.py:313-325   -> mmnas_mha_ln_*
+ *   RelSelfAtt.forward   modules.py:286-298  (RelMHAtt :224-245)                          -> mmnas_rel_mha_ln_*
+ *   FeedForward.forward  modules.py:351-362  (MLP :40-41, FC :24-31)                      -> mmnas_ffn_ln_*
+ * The descriptor is a plain C struct of device pointers, sizes and scalars; the library allocates nothing: every
+ * intermediate lives in a caller-provided workspace whose size mmnas_*_workspace() reports.  `workspace` is written
+ * by the forward and must be handed unchanged to the backward (it holds the saved activations: fused projections,
+ * attention output, z = x + dropout(branch), LayerNorm statistics, relation bias); `bwd_workspace` is scratch of the
+ * backward only.  Both need 256-byte alignment.  The fork / join uses a process-wide ring of timing-disabled CUDA
+ * events owned by the library (capturable in a CUDA graph).
+ * ========================================================================================================= */
+typedef struct mmnas_att_block {
+  /* configuration */
+  int precision;               /* 0 = fp32 arm (FFMA kernels), 1 = bf16 arm (tcgen05 kernels) */
+  int B, Nq, Nk, H, I;         /* B samples, Nq query / Nk key tokens per sample, hidden H, inner width I = heads * 64 */
+  int R;                       /* relation-embedding width (64) for RSA, 0 otherwise */
+  int residual;                /* 1: out = LN(x + dropout(branch)); 0: out = LN(dropout(branch)) */
+  int guided;                  /* 1: keys / values come from `kv` (GuidedAtt); 0: self-attention (Nk == Nq) */
+  int accumulate_grads;        /* backward: 1 = weight / LN / linear_r gradient buffers hold running sums (+=), 0 = overwrite */
+  int accumulate_geometry;     /* backward: same for dWy / dby (linear_y_rel is shared by every RSA block of a net) */
+  int accumulate_dkv;          /* backward, guided: 1 = dkv += (every GuidedAtt block of a decoder adds into ONE encoder-output gradient) */
+  float eps;                   /* LayerNorm eps (added to sigma) */
+  float p_att, p_out;          /* dropout probability of the attention map / of the block output; 0 = off */
+  unsigned long long salt_att, salt_out;
+  const unsigned long long* rng_state;   /* device {seed, step}; NULL = dropout off */
+  /* inputs */
+  const float* x;              /* [B*Nq, H] fp32 */
+  const void* x16;             /* bf16 copy of x, or NULL (bf16 arm: cast into the workspace) */
+  const float* kv;             /* guided: [B*Nk, H] fp32 */
+  const void* kv16;
+  const unsigned char* kmask;  /* [B, Nk] bytes, 1 = padded key; NULL = no mask */
+  /* parameters: fp32 masters (always) and, in the bf16 arm, bf16 copies stacked per fused GEMM */
+  const float *Wq, *Wk, *Wv, *Wm;        /* [I,H] x3, [H,I] */
+  const void* w16_a;           /* self: [Wv;Wk;Wq] as [3I,H];  guided: Wq [I,H] */
+  const void* w16_b;           /* guided: [Wv;Wk] as [2I,H];   self: unused */
+  const void* w16_m;           /* [H,I] */
+  const float *ln_a, *ln_b;    /* LayerNorm a_2 / b_2, both NULL = norm off */
+  const float *rel;            /* RSA, dense mode: rel_embed [B,Nq,Nq,R] */
+  const float *g4, *Wy, *by;   /* RSA, geometry mode: [B,Nq,Nq,4] + linear_y_rel [R,4], [R] */
+  const float *Wr, *br;        /* RSA: linear_r [heads,R], [heads] */
+  /* outputs */
+  float* out;                  /* [B*Nq, H] fp32 */
+  void* out16;                 /* optional bf16 copy of out (next block's GEMM operand) */
+  void* workspace;
+  /* backward */
+  const float* dout;           /* [B*Nq, H] */
+  float* dx;                   /* [B*Nq, H], written */
+  float* dkv;                  /* guided: [B*Nk, H], written */
+  float *dWq, *dWk, *dWv, *dWm, *dln_a, *dln_b, *dWy, *dby, *dWr, *dbr;
+  float* drel;                 /* dense mode: [B,Nq,Nq,R], written */
+  void* bwd_workspace;
+  mmnas_stream stream;
+  mmnas_stream side_stream;    /* bf16-arm weight-gradient GEMMs run here, concurrently; NULL = everything on `stream` */
+} mmnas_att_block;
+
+typedef struct mmnas_ffn_block {
+  int precision;
+  int M, H, F;                 /* M tokens, hidden H, mid size F */
+  int residual;
+  int accumulate_grads;
+  float eps;
+  float p_mid, p_out;          /* dropout of the hidden activation (FC :29) / of the block output (:353) */
+  unsigned long long salt_mid, salt_out;
+  const unsigned long long* rng_state;
+  const float* x; const void* x16;
+  const float *W1, *b1, *W2, *b2;        /* mlp.fc.linear [F,H],[F]; mlp.linear [H,F],[H] */
+  const void *w16_1, *w16_2;
+  const float *ln_a, *ln_b;
+  float* out; void* out16;
+  void* workspace;
+  const float* dout; float* dx;
+  float *dW1, *db1, *dW2, *db2, *dln_a, *dln_b;
+  void* bwd_workspace;
+  mmnas_stream stream, side_stream;
+} mmnas_ffn_block;
+
+/* sizeof() of the two descriptors as compiled into the library (bindings check their mirror structs against it) */
+int mmnas_att_block_sizeof(void);
+int mmnas_ffn_block_sizeof(void);
+/* bytes of `workspace` / `bwd_workspace` for this configuration (only the configuration fields are read) */
+int mmnas_att_block_workspace(const mmnas_att_block* d, unsigned long long* fwd_bytes, unsigned long long* bwd_bytes);
+int mmnas_ffn_block_workspace(const mmnas_ffn_block* d, unsigned long long* fwd_bytes, unsigned long long* bwd_bytes);
+/* SelfAtt / GuidedAtt (d->R must be 0) */
+int mmnas_mha_ln_fwd(const mmnas_att_block* d);
+int mmnas_mha_ln_bwd(const mmnas_att_block* d);
+/* RelSelfAtt (d->R == 64, exactly one of rel / g4 given) */
+int mmnas_rel_mha_ln_fwd(const mmnas_att_block* d);
+int mmnas_rel_mha_ln_bwd(const mmnas_att_block* d);
+/* FeedForward */
+int mmnas_ffn_ln_fwd(const mmnas_ffn_block* d);
+int mmnas_ffn_ln_bwd(const mmnas_ffn_block* d);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libmmnas_b200.so')
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 c_p, c_i, c_l, c_f, c_u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float, ctypes.c_ulonglong
 
@@ -40,6 +40,38 @@ SIGNATURES = {
     'mmnas_rng_advance': [c_p, c_p],
 }
 
+
+
+class AttBlock(ctypes.Structure):
+    """Mirror of `mmnas_att_block` (include/mmnas_b200.h): descriptor of one SelfAtt / GuidedAtt / RelSelfAtt call."""
+    _fields_ = ([(n, c_i) for n in ('precision', 'B', 'Nq', 'Nk', 'H', 'I', 'R', 'residual', 'guided', 'accumulate_grads',
+                                    'accumulate_geometry', 'accumulate_dkv')] +
+                [(n, c_f) for n in ('eps', 'p_att', 'p_out')] +
+                [(n, c_u64) for n in ('salt_att', 'salt_out')] +
+                [(n, c_p) for n in ('rng_state', 'x', 'x16', 'kv', 'kv16', 'kmask', 'Wq', 'Wk', 'Wv', 'Wm', 'w16_a', 'w16_b',
+                                    'w16_m', 'ln_a', 'ln_b', 'rel', 'g4', 'Wy', 'by', 'Wr', 'br', 'out', 'out16', 'workspace',
+                                    'dout', 'dx', 'dkv', 'dWq', 'dWk', 'dWv', 'dWm', 'dln_a', 'dln_b', 'dWy', 'dby', 'dWr',
+                                    'dbr', 'drel', 'bwd_workspace', 'stream', 'side_stream')])
+
+
+class FfnBlock(ctypes.Structure):
+    """Mirror of `mmnas_ffn_block`: descriptor of one FeedForward call."""
+    _fields_ = ([(n, c_i) for n in ('precision', 'M', 'H', 'F', 'residual', 'accumulate_grads')] +
+                [(n, c_f) for n in ('eps', 'p_mid', 'p_out')] +
+                [(n, c_u64) for n in ('salt_mid', 'salt_out')] +
+                [(n, c_p) for n in ('rng_state', 'x', 'x16', 'W1', 'b1', 'W2', 'b2', 'w16_1', 'w16_2', 'ln_a', 'ln_b', 'out',
+                                    'out16', 'workspace', 'dout', 'dx', 'dW1', 'db1', 'dW2', 'db2', 'dln_a', 'dln_b',
+                                    'bwd_workspace', 'stream', 'side_stream')])
+
+
+_pAtt, _pFfn, _pU64 = ctypes.POINTER(AttBlock), ctypes.POINTER(FfnBlock), ctypes.POINTER(c_u64)
+SIGNATURES.update({
+    'mmnas_att_block_workspace': [_pAtt, _pU64, _pU64],
+    'mmnas_ffn_block_workspace': [_pFfn, _pU64, _pU64],
+    'mmnas_mha_ln_fwd': [_pAtt], 'mmnas_mha_ln_bwd': [_pAtt],
+    'mmnas_rel_mha_ln_fwd': [_pAtt], 'mmnas_rel_mha_ln_bwd': [_pAtt],
+    'mmnas_ffn_ln_fwd': [_pFfn], 'mmnas_ffn_ln_bwd': [_pFfn],
+})
 _lib = None
 
 
@@ -58,6 +90,7 @@ def load():
             'PyTorch fallback for the operator hot path.' % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
     lib.mmnas_abi_version.restype = c_i
+    lib.mmnas_launch_count.restype = c_u64
     lib.mmnas_last_error.restype = ctypes.c_char_p
     if lib.mmnas_abi_version() != ABI_VERSION:
         raise MMnasLibraryError('libmmnas_b200.so ABI %d != binding ABI %d; rebuild' % (lib.mmnas_abi_version(), ABI_VERSION))
@@ -65,18 +98,50 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = c_i
+    for name, cls in (('mmnas_att_block_sizeof', AttBlock), ('mmnas_ffn_block_sizeof', FfnBlock)):
+        getattr(lib, name).restype = c_i
+        if getattr(lib, name)() != ctypes.sizeof(cls):
+            raise MMnasLibraryError('%s() = %d but the ctypes mirror has %d bytes: header and binding disagree'
+                                    % (name, getattr(lib, name)(), ctypes.sizeof(cls)))
     _lib = lib
     return lib
 
 
-LAUNCHES = 0          # number of C-ABI kernel entry points invoked (bench.py's `gpu_launches` claim)
+def workspace_bytes(desc):
+    """(forward workspace bytes, backward scratch bytes) of a block descriptor."""
+    fwd, bwd = c_u64(0), c_u64(0)
+    name = 'mmnas_att_block_workspace' if isinstance(desc, AttBlock) else 'mmnas_ffn_block_workspace'
+    rc = getattr(load(), name)(ctypes.byref(desc), ctypes.byref(fwd), ctypes.byref(bwd))
+    if rc != 0:
+        raise MMnasLibraryError('%s failed (%d): %s' % (name, rc, load().mmnas_last_error().decode()))
+    return fwd.value, bwd.value
+
+
+def call_block(name, desc):
+    """One block-level foreign call."""
+    lib = load()
+    if _profile is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(ctypes.byref(desc))
+        e1.record()
+        _profile.append((name, desc, e0, e1))
+    else:
+        rc = getattr(lib, name)(ctypes.byref(desc))
+    if rc != 0:
+        raise MMnasLibraryError('%s failed (%d): %s' % (name, rc, lib.mmnas_last_error().decode()))
+
+
+def launches():
+    """Kernels launched by the library in this process so far (counted inside the library: bench.py's `gpu_launches`)."""
+    return int(load().mmnas_launch_count())
+
+
 _profile = None       # when a list: (name, args, start_event, end_event) per call — bench.py's live kernel timing
 
 
 def call(name, *args):
-    global LAUNCHES
     lib = load()
-    LAUNCHES += 1
     if _profile is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -90,6 +90,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 bool mmnas_pdl_enabled();
+void mmnas_count_launch();      // process-wide count of kernels launched by this library (mmnas_launch_count())
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t mmnas_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
@@ -100,5 +101,6 @@ inline cudaError_t mmnas_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block,
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = mmnas_pdl_enabled() ? 1 : 0;
+  mmnas_count_launch();
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }

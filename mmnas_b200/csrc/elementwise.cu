@@ -2,6 +2,7 @@
 // column sums (bias gradients), the supernet mixed-op accumulate and its alpha-gate gradient
 // (mixed.py:60-68 and the autograd rule SURVEY §8 a11), and the dropout step counter.
 // All are vectorised (float4 / 8-byte bf16x4), grid-stride, grid = k x 148 SMs.
+#include <atomic>
 #include <cstdlib>
 #include "common.cuh"
 #include "../../include/mmnas_b200.h"
@@ -375,10 +376,15 @@ extern "C" int mmnas_clip_adam(const void* table, int n_chunks, const float* sum
 
 extern "C" int mmnas_rng_advance(unsigned long long* state, mmnas_stream stream) {
   MMNAS_CHECK_ARG(state, "rng_advance: null state");
+  mmnas_count_launch();
   rng_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state);
   MMNAS_LAUNCH_CHECK();
   return MMNAS_OK;
 }
+
+static std::atomic<unsigned long long> g_launches{0};
+void mmnas_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" unsigned long long mmnas_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 bool mmnas_pdl_enabled() {
   static int on = -1;

@@ -1,4 +1,4 @@
-// RSA geometry bias on the tensor cores (bf16 arm, geometry mode, 8 heads) — the warp-level companion of relbias.cu.
+// RSA geometry bias on the tensor cores (bf16 arm, geometry mode, 2 / 4 / 6 / 8 heads: H = 512 train, H = 256 search) — the warp-level companion of relbias.cu.
 //
 //   e_c   = relu(W_y[c,:] . g + b_y[c])                 64 channels per (i,j) pair      (full_vqa.py:82,103)
 //   r_h   = W_r[h,:] . e + b_r[h]                        8 heads                         (modules.py:231)
@@ -35,6 +35,7 @@ constexpr int THREADS = WARPS * 32;
 
 struct MmaArgs {
   unsigned pairs, nn;
+  int heads;                 // even, <= 8: the head axis is the n = 8 (or k = 8 of 16) axis of the fragments, zero padded
   const float *g4, *Wy, *by, *Wr, *br;
   float* bias;
   const float* dbias;
@@ -84,16 +85,19 @@ __global__ void __launch_bounds__(THREADS, 2) relbias_mma_kernel(MmaArgs a) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const float* w = a.Wr + g * R + 16 * k + 2 * q;
-    split_bf16(__ldg(w), __ldg(w + 1), wr_hi[k][0], wr_lo[k][0]);
-    split_bf16(__ldg(w + 8), __ldg(w + 9), wr_hi[k][1], wr_lo[k][1]);
+    const bool hv = g < a.heads;                   // heads past `heads`: zero columns
+    split_bf16(hv ? __ldg(w) : 0.f, hv ? __ldg(w + 1) : 0.f, wr_hi[k][0], wr_lo[k][0]);
+    split_bf16(hv ? __ldg(w + 8) : 0.f, hv ? __ldg(w + 9) : 0.f, wr_hi[k][1], wr_lo[k][1]);
   }
   // B fragments of d e = d pre_r W_r: K = heads (8, padded to 16), n-tile n covers channels 8n..8n+7; column = channel 8n+g
   uint32_t wde[8];
   if (BWD) {
 #pragma unroll
-    for (int n = 0; n < 8; ++n) wde[n] = pack_bf16(__ldg(a.Wr + (2 * q) * R + 8 * n + g), __ldg(a.Wr + (2 * q + 1) * R + 8 * n + g));
+    for (int n = 0; n < 8; ++n)
+      wde[n] = 2 * q < a.heads ? pack_bf16(__ldg(a.Wr + (2 * q) * R + 8 * n + g), __ldg(a.Wr + (2 * q + 1) * R + 8 * n + g)) : 0u;
   }
-  const float br0 = __ldg(a.br + 2 * q), br1 = __ldg(a.br + 2 * q + 1);
+  const bool myheads = 2 * q < a.heads;            // this thread's head pair (2q, 2q+1) exists
+  const float br0 = myheads ? __ldg(a.br + 2 * q) : 0.f, br1 = myheads ? __ldg(a.br + 2 * q + 1) : 0.f;
   float accWr[4][4], accWy[4][4], accbr0 = 0.f, accbr1 = 0.f;
 #pragma unroll
   for (int m = 0; m < 4; ++m)
@@ -130,10 +134,10 @@ __global__ void __launch_bounds__(THREADS, 2) relbias_mma_kernel(MmaArgs a) {
 #pragma unroll
       for (int rh = 0; rh < 2; ++rh) {
         const unsigned d = 16 * mt + 8 * rh + g;
-        live[mt][rh] = base + d < a.pairs;
+        live[mt][rh] = base + d < a.pairs && myheads;
         unsigned b = bb, ij = ij_base + d;
         while (ij >= a.nn) { ij -= a.nn; ++b; }
-        off[mt][rh] = ((size_t)b * HEADS + 2 * q) * a.nn + ij;
+        off[mt][rh] = ((size_t)b * a.heads + 2 * q) * a.nn + ij;
         gv[mt][rh] = gnext[mt][rh];
         if (BWD) {        // issued early: latency hides behind the first layer
           db[mt][rh][0] = live[mt][rh] ? __ldg(a.dbias + off[mt][rh]) : 0.f;
@@ -245,7 +249,7 @@ __global__ void __launch_bounds__(THREADS, 2) relbias_mma_kernel(MmaArgs a) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int c = 16 * m + g + 8 * (i >> 1), col = 2 * q + (i & 1);
-      atomicAdd(&sWr[col * R + c], accWr[m][i]);
+      if (col < a.heads) atomicAdd(&sWr[col * R + c], accWr[m][i]);
       if (col < 4) atomicAdd(&sWyr[c * 4 + col], accWy[m][i]);
       else if (col == 4) atomicAdd(&sbyr[c], accWy[m][i]);
     }
@@ -255,12 +259,12 @@ __global__ void __launch_bounds__(THREADS, 2) relbias_mma_kernel(MmaArgs a) {
     accbr0 += __shfl_xor_sync(0xffffffffu, accbr0, off);
     accbr1 += __shfl_xor_sync(0xffffffffu, accbr1, off);
   }
-  if (g == 0) { atomicAdd(&sbr[2 * q], accbr0); atomicAdd(&sbr[2 * q + 1], accbr1); }
+  if (g == 0 && myheads) { atomicAdd(&sbr[2 * q], accbr0); atomicAdd(&sbr[2 * q + 1], accbr1); }
   __syncthreads();
-  for (int i = tid; i < R * HEADS; i += THREADS) atomicAdd(&a.dWr[i], sWr[i]);
+  for (int i = tid; i < R * a.heads; i += THREADS) atomicAdd(&a.dWr[i], sWr[i]);
   for (int i = tid; i < R * 4; i += THREADS) atomicAdd(&a.dWy[i], sWyr[i]);
   for (int i = tid; i < R; i += THREADS) atomicAdd(&a.dby[i], sbyr[i]);
-  if (tid < HEADS) atomicAdd(&a.dbr[tid], sbr[tid]);
+  if (tid < a.heads) atomicAdd(&a.dbr[tid], sbr[tid]);
 }
 
 int grid_for(unsigned pairs, unsigned pairs_per_iter, unsigned ctas_per_sm) {
@@ -274,9 +278,10 @@ int grid_for(unsigned pairs, unsigned pairs_per_iter, unsigned ctas_per_sm) {
 // Returns MMNAS_ERR_UNSUPPORTED when the configuration is outside this kernel (caller then uses relbias.cu).
 int mmnas_relbias_fwd_mma(int B, int N, int heads, const float* g4, const float* Wy, const float* by, const float* Wr,
                           const float* br, float* bias, cudaStream_t s) {
-  if (heads != HEADS || !g4 || ((uintptr_t)g4 % 16) != 0 || ((uintptr_t)Wy % 16) != 0) return MMNAS_ERR_UNSUPPORTED;
+  if (heads > HEADS || heads < 2 || (heads & 1) || !g4 || ((uintptr_t)g4 % 16) != 0 || ((uintptr_t)Wy % 16) != 0) return MMNAS_ERR_UNSUPPORTED;
   MmaArgs a = {};
   a.nn = (unsigned)N * N; a.pairs = (unsigned)B * a.nn;
+  a.heads = heads;
   a.g4 = g4; a.Wy = Wy; a.by = by; a.Wr = Wr; a.br = br; a.bias = bias;
   MMNAS_CUDA(mmnas_launch(relbias_mma_kernel<false, 2>, dim3(grid_for(a.pairs, 32, 2)), dim3(THREADS), 0, s, a));
   return MMNAS_OK;
@@ -285,9 +290,10 @@ int mmnas_relbias_fwd_mma(int B, int N, int heads, const float* g4, const float*
 int mmnas_relbias_bwd_mma(int B, int N, int heads, const float* g4, const float* Wy, const float* by, const float* Wr,
                           const float* br, const float* dbias, float* dWy, float* dby, float* dWr, float* dbr,
                           cudaStream_t s) {
-  if (heads != HEADS || !g4 || ((uintptr_t)g4 % 16) != 0 || ((uintptr_t)Wy % 16) != 0) return MMNAS_ERR_UNSUPPORTED;
+  if (heads > HEADS || heads < 2 || (heads & 1) || !g4 || ((uintptr_t)g4 % 16) != 0 || ((uintptr_t)Wy % 16) != 0) return MMNAS_ERR_UNSUPPORTED;
   MmaArgs a = {};
   a.nn = (unsigned)N * N; a.pairs = (unsigned)B * a.nn;
+  a.heads = heads;
   a.g4 = g4; a.Wy = Wy; a.by = by; a.Wr = Wr; a.br = br; a.dbias = dbias;
   a.dWy = dWy; a.dby = dby; a.dWr = dWr; a.dbr = dbr;
   MMNAS_CUDA(mmnas_launch(relbias_mma_kernel<true, 1>, dim3(grid_for(a.pairs, 16, 2)), dim3(THREADS), 0, s, a));

@@ -411,7 +411,7 @@ class TrainStep:
         if runtime.get_precision() == 'bf16':
             self.shadows.refresh()
             runtime.shadows_fresh = True
-        runtime.direct_grads, runtime.grad_listener = True, self.reducer.notify
+        runtime.direct_grads, runtime.grad_listener = True, (self.reducer.notify if self.reducer.enabled else None)
         try:
             pred = self.net(inputs)
             loss = self.loss_fn(pred, target)
@@ -481,7 +481,7 @@ class SearchStep:
     architecture step in MODE 'full' on a held-out batch."""
 
     def __init__(self, net, lr_base=0.0004, epoch_steps=1000, alpha_lr=0.1, alpha_betas=(0., 0.999), mode='full',
-                 bucket_mb=25.0, loss_fn=vqa_loss):
+                 bucket_mb=25.0, loss_fn=vqa_loss, use_executor=True):
         self.net = net
         self.mode = mode
         self.loss_fn = loss_fn
@@ -493,6 +493,12 @@ class SearchStep:
         self.alpha_optim = torch.optim.Adam(list(net.alpha_prob_parameters()), alpha_lr, betas=alpha_betas,
                                             weight_decay=0)
         self.shadows = WeightShadows(net)       # every candidate's GEMM weights, one batched cast per step
+        # static-plan executor of the supernet backbone (executor.py): one autograd node, one foreign call per block
+        self.executor = None
+        if use_executor and self.net_params[0].is_cuda and mode == 'full':
+            from .executor import SearchExecutor
+            self.executor = SearchExecutor(net)
+        object.__setattr__(net, '_executor', self.executor)
 
     def _forward_backward(self, inputs, target):
         self.grads.zero()                # net.zero_grad() + the reference's 0*sum(params) dummy terms
@@ -501,7 +507,7 @@ class SearchStep:
         if runtime.get_precision() == 'bf16':
             self.shadows.refresh()
             runtime.shadows_fresh = True
-        runtime.direct_grads, runtime.grad_listener = True, self.reducer.notify
+        runtime.direct_grads, runtime.grad_listener = True, (self.reducer.notify if self.reducer.enabled else None)
         try:
             loss = self.loss_fn(self.net(inputs), target)
             loss.backward()
@@ -511,30 +517,41 @@ class SearchStep:
         self.reducer.finish()
         return loss.detach()
 
+    def _off(self):
+        # Net_Search.unused_modules_off/back (hygr_vqa.py:175-196) swap the candidates that do not run for None; the
+        # executor addresses candidates through its static plans and never touches the others, so the 130 module-list
+        # writes per step are skipped when it is active
+        if self.executor is None:
+            self.net.unused_modules_off()
+
+    def _back(self):
+        if self.executor is None:
+            self.net.unused_modules_back()
+
     def weight_step(self, inputs, target):
         MixedOp.MODE = None
         self.net.reset_binary_gates(batched=True)
-        self.net.unused_modules_off()
+        self._off()
         try:
             self.optim.set_lr()
             loss = self._forward_backward(inputs, target)
             self.optim.clip_and_step()
         finally:
-            self.net.unused_modules_back()
+            self._back()
         return loss
 
     def arch_step(self, inputs, target):
         MixedOp.MODE = self.mode
         self.net.reset_binary_gates(batched=(self.mode != 'two'))
-        self.net.unused_modules_off()
+        self._off()
         try:
             loss = self._forward_backward(inputs, target)
-            self.net.set_arch_param_grad()
+            self.net.set_arch_param_grad(batched=True)
             self.alpha_optim.step()
             if MixedOp.MODE == 'two':
                 self.net.rescale_updated_arch_param()
         finally:
-            self.net.unused_modules_back()
+            self._back()
             MixedOp.MODE = None
         return loss
 

@@ -159,8 +159,10 @@ def _bf16(t, shadow):
 # ----------------------------------------------------------------------------------------------------------
 # attention blocks: SelfAtt / RelSelfAtt / GuidedAtt  (modules.py:248-325 over MHAtt :158-199, RelMHAtt :202-245)
 # ----------------------------------------------------------------------------------------------------------
-class AttBlockFn(Function):
-    """out = LN(x + dropout(merge(att(q(x), k(kv), v(kv)))));  kv=None means self-attention (kv is x)."""
+class AttBlockPyFn(Function):
+    """out = LN(x + dropout(merge(att(q(x), k(kv), v(kv)))));  kv=None means self-attention (kv is x).
+    The block composed from the PRIMITIVE entry points, one foreign call per kernel (runtime.compose_in_python): the
+    decomposed path bench.py times kernel by kernel, and the cross-check of the C-composed block (AttBlockFn)."""
 
     @staticmethod
     def forward(ctx, x, kv, Wq, Wk, Wv, Wm, a2, b2, rel, g4, Wy, by, Wr, br, cfg):
@@ -364,8 +366,8 @@ class AttBlockFn(Function):
 # ----------------------------------------------------------------------------------------------------------
 # FeedForward  (modules.py:328-362 over MLP :34-41 / FC :13-31)
 # ----------------------------------------------------------------------------------------------------------
-class FFNBlockFn(Function):
-    """out = LN(x + dropout(W2 dropout(relu(W1 x + b1)) + b2))"""
+class FFNBlockPyFn(Function):
+    """out = LN(x + dropout(W2 dropout(relu(W1 x + b1)) + b2)) composed from the primitive entry points (see AttBlockPyFn)."""
 
     @staticmethod
     def forward(ctx, x, W1, b1, W2, b2f, a2, b2, cfg):
@@ -462,6 +464,254 @@ class FFNBlockFn(Function):
         fork.join()
         return (dz.view(B, N, H), s_W1.grads()[0], s_bias1.grads()[0], s_W2.grads()[0], s_bias2.grads()[0],
                 s_a2.grads()[0] if norm else None, s_b2.grads()[0] if norm else None, None)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Block-level calls (ABI v7): one foreign call per block forward / backward.  The C side (csrc/blocks.cu) carves
+# the workspace, orders the launches and forks the weight-gradient GEMMs onto the side stream.
+# ----------------------------------------------------------------------------------------------------------
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _direct(params):
+    """Gradient destinations for direct accumulation: every parameter owns a preset contiguous fp32 .grad (a view of
+    engine.FlatGrads) and none is shared between blocks.  Returns the .grad tensors or None."""
+    if not runtime.direct_grads:
+        return None
+    out = []
+    for p in params:
+        if p is None:
+            out.append(None)
+            continue
+        g = p.grad
+        if g is None or g.dtype != torch.float32 or not g.is_contiguous() or getattr(p, '_mmnas_shared', False):
+            return None
+        out.append(g)
+    return out
+
+
+def _side_stream(dev, bf):
+    if bf and runtime.overlap_wgrad:
+        return runtime.side_stream(dev).cuda_stream
+    return None
+
+
+class AttBlockFn(Function):
+    """SelfAtt / GuidedAtt / RelSelfAtt as ONE foreign call per direction (mmnas_mha_ln_* / mmnas_rel_mha_ln_*)."""
+
+    @staticmethod
+    def forward(ctx, x, kv, Wq, Wk, Wv, Wm, a2, b2, rel, g4, Wy, by, Wr, br, cfg):
+        require_cuda(x, kv, Wq)
+        ctx.set_materialize_grads(False)
+        dev = x.device
+        x = x.contiguous()
+        B, Nq, H = x.shape
+        I = Wq.shape[0]
+        guided = kv is not None
+        kvt = kv.contiguous() if guided else None
+        Nk = kvt.shape[1] if guided else Nq
+        bf = cfg.precision == 'bf16'
+        d_att, d_out = cfg.drops
+        d = _lib.AttBlock()
+        d.precision = 1 if bf else 0
+        d.B, d.Nq, d.Nk, d.H, d.I = B, Nq, Nk, H, I
+        d.R = Wr.shape[1] if Wr is not None else 0
+        d.residual = 1 if cfg.residual else 0
+        d.guided = 1 if guided else 0
+        d.eps = cfg.eps
+        st = d_att.state if d_att.active else (d_out.state if d_out.active else None)
+        if st is not None:
+            d.rng_state = st.data_ptr()
+            if d_att.active:
+                d.p_att, d.salt_att = d_att.p, d_att.salt
+            if d_out.active:
+                d.p_out, d.salt_out = d_out.p, d_out.salt
+        x16 = kv16 = None
+        if bf:
+            x16 = cfg.x16
+            kv16 = cfg.kv16 if guided else None
+            w = cfg.w16
+            d.w16_a = (w['q'] if guided else w['vkq']).data_ptr()
+            if guided:
+                d.w16_b = w['vk'].data_ptr()
+            d.w16_m = w['m'].data_ptr()
+        d.x, d.x16 = x.data_ptr(), _ptr(x16)
+        if guided:
+            d.kv, d.kv16 = kvt.data_ptr(), _ptr(kv16)
+        d.kmask = _ptr(cfg.kmask)
+        d.Wq, d.Wk, d.Wv, d.Wm = Wq.data_ptr(), Wk.data_ptr(), Wv.data_ptr(), Wm.data_ptr()
+        d.ln_a, d.ln_b = _ptr(a2), _ptr(b2)
+        if d.R:
+            if g4 is not None:
+                g4 = g4.contiguous()
+                d.g4, d.Wy, d.by = g4.data_ptr(), Wy.data_ptr(), by.data_ptr()
+            else:
+                rel = rel.contiguous()
+                d.rel = rel.data_ptr()
+            d.Wr, d.br = Wr.data_ptr(), br.data_ptr()
+        fwd_bytes, bwd_bytes = _lib.workspace_bytes(d)
+        ws = torch.empty(fwd_bytes, dtype=torch.uint8, device=dev)
+        out = torch.empty((B, Nq, H), dtype=torch.float32, device=dev)
+        out16 = torch.empty((B, Nq, H), dtype=torch.bfloat16, device=dev) if bf else None
+        d.out, d.out16, d.workspace = out.data_ptr(), _ptr(out16), ws.data_ptr()
+        d.stream = _lib.stream()
+        _lib.call_block('mmnas_rel_mha_ln_fwd' if d.R else 'mmnas_mha_ln_fwd', d)
+        ctx.desc, ctx.bwd_bytes, ctx.guided, ctx.bf = d, bwd_bytes, guided, bf
+        ctx.params = (Wq, Wk, Wv, Wm, a2, b2, Wr, br)
+        ctx.geo = (Wy, by)
+        ctx.save_for_backward(x, kvt, rel, g4, ws, x16, kv16, cfg.kmask)
+        ctx.w16 = cfg.w16            # keeps the bf16 weight copies alive until the backward has run
+        if bf:
+            ctx.mark_non_differentiable(out16)
+            return out, out16
+        return out, None
+
+    @staticmethod
+    def backward(ctx, dout, _unused=None):
+        if dout is None:
+            return (None,) * 15
+        d = ctx.desc
+        x, kvt, rel, g4, ws, x16, kv16, kmask = ctx.saved_tensors
+        Wq, Wk, Wv, Wm, a2, b2, Wr, br = ctx.params
+        Wy, by = ctx.geo
+        dev = x.device
+        B, Nq, Nk, H, I = d.B, d.Nq, d.Nk, d.H, d.I
+        dout = dout.contiguous()
+        dx = torch.empty((B, Nq, H), dtype=torch.float32, device=dev)
+        dkv = torch.empty((B, Nk, H), dtype=torch.float32, device=dev) if ctx.guided else None
+        bws = torch.empty(ctx.bwd_bytes, dtype=torch.uint8, device=dev)
+        own = (Wv, Wk, Wq, Wm, a2, b2, Wr, br)
+        sinks = _direct(own)
+        direct = sinks is not None
+        if not direct:
+            f32 = dict(dtype=torch.float32, device=dev)
+            if ctx.guided:
+                gq, gvk = torch.empty((I, H), **f32), torch.empty((2 * I, H), **f32)
+                gv, gk = gvk[:I], gvk[I:]
+            else:
+                gvkq = torch.empty((3 * I, H), **f32)
+                gv, gk, gq = gvkq[:I], gvkq[I:2 * I], gvkq[2 * I:]
+            gm = torch.empty((H, I), **f32)
+            ga = gb = gr = gbr = None
+            if a2 is not None:
+                gab = torch.empty((2, H), **f32)
+                ga, gb = gab[0], gab[1]
+            if d.R:
+                grb = torch.empty((Wr.shape[0] * (d.R + 1),), **f32)
+                gr, gbr = grb[:Wr.numel()].view_as(Wr), grb[Wr.numel():]
+            sinks = [gv, gk, gq, gm, ga, gb, gr, gbr]
+        d.accumulate_grads = 1 if direct else 0
+        d.dWv, d.dWk, d.dWq, d.dWm = (sinks[i].data_ptr() for i in range(4))
+        d.dln_a, d.dln_b, d.dWr, d.dbr = _ptr(sinks[4]), _ptr(sinks[5]), _ptr(sinks[6]), _ptr(sinks[7])
+        gy = gby = drel = None
+        if d.R:
+            if g4 is not None:
+                geo = _direct((Wy, by))
+                if geo is not None:
+                    d.accumulate_geometry, gyb = 1, None
+                    d.dWy, d.dby = geo[0].data_ptr(), geo[1].data_ptr()
+                else:                   # linear_y_rel is shared by every RSA block: autograd sums the contributions
+                    d.accumulate_geometry = 0
+                    gyb = torch.empty((d.R * 5,), dtype=torch.float32, device=dev)
+                    gy, gby = gyb[:d.R * 4].view(d.R, 4), gyb[d.R * 4:]
+                    d.dWy, d.dby = gy.data_ptr(), gby.data_ptr()
+            else:
+                drel = torch.empty_like(rel)
+                d.drel = drel.data_ptr()
+        d.dout, d.dx, d.dkv, d.bwd_workspace = dout.data_ptr(), dx.data_ptr(), _ptr(dkv), bws.data_ptr()
+        d.stream = _lib.stream()
+        d.side_stream = _side_stream(dev, ctx.bf)
+        _lib.call_block('mmnas_rel_mha_ln_bwd' if d.R else 'mmnas_mha_ln_bwd', d)
+        if direct:
+            runtime.notify_grads(own)
+            if d.R and g4 is not None and d.accumulate_geometry:
+                runtime.notify_grads((Wy, by))
+            gv = gk = gq = gm = ga = gb = gr = gbr = None
+        else:
+            gv, gk, gq, gm, ga, gb, gr, gbr = sinks
+        return (dx, dkv, gq, gk, gv, gm, ga, gb, drel, None, gy, gby, gr, gbr, None)
+
+
+class FFNBlockFn(Function):
+    """FeedForward as ONE foreign call per direction (mmnas_ffn_ln_fwd / mmnas_ffn_ln_bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, W1, b1, W2, b2f, a2, b2, cfg):
+        require_cuda(x, W1)
+        ctx.set_materialize_grads(False)
+        dev = x.device
+        x = x.contiguous()
+        B, N, H = x.shape
+        bf = cfg.precision == 'bf16'
+        d_mid, d_out = cfg.drops
+        d = _lib.FfnBlock()
+        d.precision = 1 if bf else 0
+        d.M, d.H, d.F = B * N, H, W1.shape[0]
+        d.residual = 1 if cfg.residual else 0
+        d.eps = cfg.eps
+        st = d_mid.state if d_mid.active else (d_out.state if d_out.active else None)
+        if st is not None:
+            d.rng_state = st.data_ptr()
+            if d_mid.active:
+                d.p_mid, d.salt_mid = d_mid.p, d_mid.salt
+            if d_out.active:
+                d.p_out, d.salt_out = d_out.p, d_out.salt
+        x16 = None
+        if bf:
+            x16 = cfg.x16
+            d.w16_1, d.w16_2 = cfg.w16['w1'].data_ptr(), cfg.w16['w2'].data_ptr()
+        d.x, d.x16 = x.data_ptr(), _ptr(x16)
+        d.W1, d.b1, d.W2, d.b2 = W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2f.data_ptr()
+        d.ln_a, d.ln_b = _ptr(a2), _ptr(b2)
+        fwd_bytes, bwd_bytes = _lib.workspace_bytes(d)
+        ws = torch.empty(fwd_bytes, dtype=torch.uint8, device=dev)
+        out = torch.empty((B, N, H), dtype=torch.float32, device=dev)
+        out16 = torch.empty((B, N, H), dtype=torch.bfloat16, device=dev) if bf else None
+        d.out, d.out16, d.workspace = out.data_ptr(), _ptr(out16), ws.data_ptr()
+        d.stream = _lib.stream()
+        _lib.call_block('mmnas_ffn_ln_fwd', d)
+        ctx.desc, ctx.bwd_bytes, ctx.bf, ctx.shape = d, bwd_bytes, bf, (B, N, H)
+        ctx.params = (W1, b1, W2, b2f, a2, b2)
+        ctx.save_for_backward(x, ws, x16)
+        ctx.w16 = cfg.w16
+        if bf:
+            ctx.mark_non_differentiable(out16)
+            return out, out16
+        return out, None
+
+    @staticmethod
+    def backward(ctx, dout, _unused=None):
+        if dout is None:
+            return (None,) * 8
+        d = ctx.desc
+        x, ws, x16 = ctx.saved_tensors
+        W1, b1, W2, b2f, a2, b2 = ctx.params
+        dev = x.device
+        dout = dout.contiguous()
+        dx = torch.empty(ctx.shape, dtype=torch.float32, device=dev)
+        bws = torch.empty(ctx.bwd_bytes, dtype=torch.uint8, device=dev)
+        own = (W1, b1, W2, b2f, a2, b2)
+        sinks = _direct(own)
+        direct = sinks is not None
+        if not direct:
+            f32 = dict(dtype=torch.float32, device=dev)
+            sinks = [torch.empty_like(W1, dtype=torch.float32), torch.empty((d.F,), **f32),
+                     torch.empty_like(W2, dtype=torch.float32), torch.empty((d.H,), **f32), None, None]
+            if a2 is not None:
+                gab = torch.empty((2, d.H), **f32)
+                sinks[4], sinks[5] = gab[0], gab[1]
+        d.accumulate_grads = 1 if direct else 0
+        d.dW1, d.db1, d.dW2, d.db2 = (sinks[i].data_ptr() for i in range(4))
+        d.dln_a, d.dln_b = _ptr(sinks[4]), _ptr(sinks[5])
+        d.dout, d.dx, d.bwd_workspace = dout.data_ptr(), dx.data_ptr(), bws.data_ptr()
+        d.stream = _lib.stream()
+        d.side_stream = _side_stream(dev, ctx.bf)
+        _lib.call_block('mmnas_ffn_ln_bwd', d)
+        if direct:
+            runtime.notify_grads(own)
+            return (dx, None, None, None, None, None, None, None)
+        return (dx, sinks[0], sinks[1], sinks[2], sinks[3], sinks[4], sinks[5], None)
 
 
 # ----------------------------------------------------------------------------------------------------------

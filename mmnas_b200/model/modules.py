@@ -18,7 +18,7 @@ import torch.nn.functional as F
 from .. import kernels as K
 from .. import runtime
 from .._lib import require_cuda
-from ..functional import AttBlockFn, FFNBlockFn, LayerNormFn, BlockCfg
+from ..functional import AttBlockFn, AttBlockPyFn, FFNBlockFn, FFNBlockPyFn, LayerNormFn, BlockCfg
 
 
 class RelGeometry:
@@ -213,7 +213,8 @@ class MHAtt(_OpBase):
                 g4, Wy, by = rel_embed.g4, rel_embed.weight, rel_embed.bias
             else:
                 rel = rel_embed
-        out, out16 = AttBlockFn.apply(x, None if self_att else kv, self.linear_q.weight, self.linear_k.weight,
+        fn = AttBlockPyFn if runtime.compose_in_python else AttBlockFn
+        out, out16 = fn.apply(x, None if self_att else kv, self.linear_q.weight, self.linear_k.weight,
                                       self.linear_v.weight, self.linear_merge.weight,
                                       ln.a_2 if ln is not None else None, ln.b_2 if ln is not None else None,
                                       rel, g4, Wy, by, Wr, br, cfg)
@@ -312,7 +313,8 @@ class FeedForward(_OpBase):
         ln = self.ln if self.norm else None
         cfg = BlockCfg(mode, self.residual, ln.eps if ln is not None else 1e-6, self._drops(x, self.DROPOUT_R),
                        x16=_shadow(x), w16=w16)
-        out, out16 = FFNBlockFn.apply(x, w1.weight, w1.bias, w2.weight, w2.bias,
+        fn = FFNBlockPyFn if runtime.compose_in_python else FFNBlockFn
+        out, out16 = fn.apply(x, w1.weight, w1.bias, w2.weight, w2.bias,
                                       ln.a_2 if ln is not None else None, ln.b_2 if ln is not None else None, cfg)
         if out16 is not None:
             out._mmnas_bf16 = out16

@@ -134,6 +134,12 @@ class _NetBase(nn.Module):
                                              runtime.get_precision())
         # x_rel is never consumed (no relation op is an encoder candidate); the reference still embeds it in
         # Net_Search (hygr_vqa.py:130) — the parameters exist here for checkpoint parity, the dead matmul does not run.
+        ex = getattr(self, '_executor', None)
+        if ex is not None and ex.usable(self.rel_mode):
+            # engine search step: the whole supernet backbone is one autograd node over static per-candidate plans
+            from ..executor import BackboneFn
+            x_out, y_out = BackboneFn.apply(x_in, y_in, x_mask, y_mask, y_rel, ex)
+            return self.head(x_out, y_out, x_mask, y_mask)
         if self.rel_mode == 'geometry':
             y_rel = RelGeometry(y_rel, self.linear_y_rel)
         else:
@@ -207,43 +213,54 @@ class Net_Search(_NetBase):
     def reset_binary_gates(self, batched=False, group=None):
         """Sample every node's active path (MixedOp.binarize, mixed.py:131-163).
 
-        batched=True (the step harness) keeps the reference's random-number consumption — one
-        `torch.multinomial(probs, 1)` per MixedOp, in module registration order, on a [K] probability vector, exactly
-        the call sequence of hygr_vqa.py:168-172 over mixed.py:151 — so one seed draws the same path as the reference.
-        Only the bookkeeping around the draws is batched: one softmax per node width, ONE host read of all 30 picks
-        (instead of 30 `.item()` syncs), one multi-tensor copy for the one-hot gates, and the candidates' .grad buffers
-        are left alone (the harness zeroes the flat gradient buffer, which is what the reference's dummy-loss terms turn
-        the None grads into anyway).  Under data parallelism the picks are broadcast from rank 0, so every rank runs
-        the same path by construction (the reference relies on identically seeded ranks).  Not for MODE 'two'."""
+        batched=True (the step harness) keeps the reference's random-number consumption.  The reference draws
+        `torch.multinomial(probs, 1)` once per MixedOp, in module registration order (hygr_vqa.py:168-172 over
+        mixed.py:151).  For a single draw torch implements that as  q = empty_like(probs).exponential_(1);
+        argmax(probs / q)  (ATen multinomial_out, the "gumbel" fast path, CPU and CUDA alike) — the generator is
+        consumed by exactly one exponential_ call on a [K] tensor.  Here the SAME exponential_ calls are issued in the
+        same order (so one seed draws the same path as the reference: tests/test_host_logic.py checks five consecutive
+        draws against the unmodified reference), but everything around them is batched: one softmax and one argmax per
+        node width instead of seven tiny kernels per node, ONE host read of all 30 picks instead of 30 `.item()`
+        syncs, one multi-tensor copy for the one-hot gates.  The candidates' .grad buffers are left alone (the harness
+        zeroes the flat gradient buffer, which is what the reference's dummy-loss terms turn the None grads into).
+        Under data parallelism the picks are broadcast from rank 0, so every rank runs the same path by construction
+        (the reference relies on identically seeded ranks).  Not for MODE 'two'."""
         if not batched:
             for m in self.redundant_modules:
                 m.binarize()
             return
         mods = self.redundant_modules
-        with torch.no_grad():
-            rows = {}
+        plan = getattr(self, '_sample_plan', None)
+        if plan is None or plan[0] != len(mods):
             groups = {}
-            for m in mods:
-                groups.setdefault(m.n_choices, []).append(m)
-            for k, ms in groups.items():
-                probs = F.softmax(torch.stack([m.alpha_prob.data for m in ms]), dim=1)
-                for m, p in zip(ms, probs.unbind(0)):
-                    rows[id(m)] = p
-            picks = torch.cat([torch.multinomial(rows[id(m)], 1) for m in mods])
+            for i, m in enumerate(mods):
+                groups.setdefault(m.n_choices, []).append(i)
+            order = [i for k in groups for i in groups[k]]             # module index of every row of the stacked picks
+            plan = self._sample_plan = (len(mods), groups, order)
+        _, groups, order = plan
+        with torch.no_grad():
+            dev = mods[0].alpha_prob.device
+            qs = [torch.empty(m.n_choices, dtype=m.alpha_prob.dtype, device=dev).exponential_(1) for m in mods]
+            picks, onehots, gates = [], [], []
+            for k, idxs in groups.items():
+                probs = F.softmax(torch.stack([mods[i].alpha_prob.data for i in idxs]), dim=1)
+                pk = torch.argmax(probs / torch.stack([qs[i] for i in idxs]), dim=1)
+                picks.append(pk)
+            picks = torch.cat(picks)                                   # in `order`
             if group is not False and torch.distributed.is_available() and torch.distributed.is_initialized() \
                     and torch.distributed.get_world_size(group) > 1:
                 torch.distributed.broadcast(picks, 0, group=group)
-            idx = picks.tolist()
-            gates, onehots = [], []
-            pos = {id(m): i for i, m in enumerate(mods)}
-            for k, ms in groups.items():
-                oh = F.one_hot(picks[torch.tensor([pos[id(m)] for m in ms], device=picks.device)], k).to(ms[0].alpha_gate.dtype)
-                gates += [m.alpha_gate.data for m in ms]
+            off = 0
+            for k, idxs in groups.items():
+                oh = F.one_hot(picks[off:off + len(idxs)], k).to(mods[idxs[0]].alpha_gate.dtype)
+                off += len(idxs)
+                gates += [mods[i].alpha_gate.data for i in idxs]
                 onehots += list(oh.unbind(0))
             torch._foreach_copy_(gates, onehots)
-            for m, a in zip(mods, idx):
-                m.active_index = [a]
-                m.inactive_index = [i for i in range(m.n_choices) if i != a]
+            for i, a in zip(order, picks.tolist()):
+                m = mods[i]
+                object.__setattr__(m, 'active_index', [a])             # plain attributes: skip nn.Module.__setattr__
+                object.__setattr__(m, 'inactive_index', [j for j in range(m.n_choices) if j != a])
 
     def unused_modules_off(self):
         self._unused_modules = []
@@ -264,9 +281,26 @@ class Net_Search(_NetBase):
                 m.candidate_ops[i] = op
         self._unused_modules = None
 
-    def set_arch_param_grad(self):
+    def set_arch_param_grad(self, batched=False):
+        """alpha_prob.grad_i += sum_j gate.grad_j p_j (delta_ij - p_i) for every node (MixedOp.set_arch_param_grad,
+        mixed.py:171-198).  batched=True ('full' mode only) evaluates the rule for all nodes of one width at once —
+        a dozen small kernels instead of ~180."""
+        if not batched or MixedOp.MODE == 'two':
+            for m in self.redundant_modules:
+                m.set_arch_param_grad()
+            return
+        groups = {}
         for m in self.redundant_modules:
-            m.set_arch_param_grad()
+            groups.setdefault(m.n_choices, []).append(m)
+        with torch.no_grad():
+            for k, ms in groups.items():
+                for m in ms:
+                    if m.alpha_prob.grad is None:
+                        m.alpha_prob.grad = torch.zeros_like(m.alpha_prob.data)
+                p = F.softmax(torch.stack([m.alpha_prob.data for m in ms]), dim=1)
+                g = torch.stack([m.alpha_gate.grad for m in ms])
+                upd = p * (g - (g * p).sum(1, keepdim=True))
+                torch._foreach_add_([m.alpha_prob.grad for m in ms], list(upd.unbind(0)))
 
     def rescale_updated_arch_param(self):
         for m in self.redundant_modules:

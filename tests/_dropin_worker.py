@@ -88,7 +88,7 @@ def main():
                      'grads': {n: p.grad.detach().cpu() for n, p in net.named_net_parameters() if p.grad is not None}}
     if impl == 'ours':
         from mmnas_b200 import _lib
-        res['launches'] = _lib.LAUNCHES
+        res['launches'] = _lib.launches()
     torch.save(res, out_path)
 
 

@@ -16,7 +16,7 @@ HEADER = os.path.join(ROOT, 'include', 'mmnas_b200.h')
 def declared():
     src = re.sub(r'/\*.*?\*/', '', open(HEADER).read(), flags=re.S)
     out = {}
-    for m in re.finditer(r'\b(?:int|const char\*)\s+(mmnas_\w+)\s*\(([^;]*?)\)\s*;', src, flags=re.S):
+    for m in re.finditer(r'\b(?:int|const char\*|unsigned long long)\s+(mmnas_\w+)\s*\(([^;]*?)\)\s*;', src, flags=re.S):
         args = m.group(2).strip()
         out[m.group(1)] = 0 if args in ('', 'void') else len(args.split(','))
     return out
@@ -28,14 +28,52 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     from mmnas_b200 import _lib
     lib = ctypes.CDLL(_lib.LIB_PATH)
     decl = declared()
-    assert len(decl) == 19
+    assert len(decl) == 30            # 19 primitive entry points + 10 block-level ones (ABI v7)
     for name in decl:
         assert hasattr(lib, name), name
     lib.mmnas_abi_version.restype = ctypes.c_int
     assert lib.mmnas_abi_version() == _lib.ABI_VERSION
     for name, argtypes in _lib.SIGNATURES.items():
         assert decl[name] == len(argtypes), name          # binding arity == header arity
-    assert set(_lib.SIGNATURES) | {'mmnas_abi_version', 'mmnas_last_error'} == set(decl)
+    assert set(_lib.SIGNATURES) | {'mmnas_abi_version', 'mmnas_last_error', 'mmnas_launch_count', 'mmnas_att_block_sizeof',
+                                   'mmnas_ffn_block_sizeof'} == set(decl)
+    # the ctypes mirrors of the block descriptors have the size the library was compiled with
+    lib.mmnas_att_block_sizeof.restype = lib.mmnas_ffn_block_sizeof.restype = ctypes.c_int
+    assert lib.mmnas_att_block_sizeof() == ctypes.sizeof(_lib.AttBlock)
+    assert lib.mmnas_ffn_block_sizeof() == ctypes.sizeof(_lib.FfnBlock)
+    # ... and the same field names, in the header's order
+    hdr = open(HEADER).read()
+    for cname, cls in (('mmnas_att_block', _lib.AttBlock), ('mmnas_ffn_block', _lib.FfnBlock)):
+        body = re.sub(r'/\*.*?\*/', '', hdr[hdr.index('typedef struct %s {' % cname):hdr.index('} %s;' % cname)], flags=re.S)
+        names = []
+        for stmt in body.split('{', 1)[1].split(';'):
+            stmt = stmt.strip()
+            if not stmt:
+                continue
+            decls = stmt.split(',')
+            first = decls[0].split()[-1]
+            names += [first.lstrip('*')] + [x.strip().lstrip('*') for x in decls[1:]]
+        assert names == [f[0] for f in cls._fields_], cname
+
+
+def test_block_descriptor_errors_are_reported_without_a_gpu():
+    from mmnas_b200 import _lib
+    d = _lib.AttBlock()
+    d.precision, d.B, d.Nq, d.Nk, d.H, d.I, d.R = 1, 2, 10, 10, 128, 100, 0
+    with pytest.raises(_lib.MMnasLibraryError, match='multiple of the head dim'):
+        _lib.call_block('mmnas_mha_ln_fwd', d)
+    d.I, d.R = 128, 64
+    with pytest.raises(_lib.MMnasLibraryError, match='relation inputs given'):
+        _lib.call_block('mmnas_mha_ln_fwd', d)
+    with pytest.raises(_lib.MMnasLibraryError, match='exactly one of rel / g4'):
+        _lib.call_block('mmnas_rel_mha_ln_fwd', d)
+    d.R = 0
+    fwd, bwd = _lib.workspace_bytes(d)
+    assert fwd % 256 == 0 and bwd % 256 == 0 and fwd >= 2 * 20 * (3 * 128 + 128) + 4 * 20 * 128
+    f = _lib.FfnBlock()
+    f.precision, f.M, f.H, f.F = 0, 20, 128, 512
+    with pytest.raises(_lib.MMnasLibraryError, match='null input'):
+        _lib.call_block('mmnas_ffn_ln_fwd', f)
 
 
 def test_argument_errors_are_reported_without_a_gpu():

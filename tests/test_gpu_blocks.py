@@ -268,3 +268,43 @@ def test_mixed_op_two_mode_matches_reference_golden(mode):
         elif n_.startswith('candidate_ops.'):
             assert p_.grad is None, n_
     pr.check()
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+@pytest.mark.parametrize('name,nx,ny', [('self_att_64', 100, 14), ('self_att_64', 14, 100), ('rel_self_att_64', 100, 14),
+                                        ('guided_att_64', 100, 14), ('guided_att_64', 36, 50), ('feed_forward', 100, 14)])
+def test_block_level_c_calls_equal_the_python_composition(name, nx, ny, mode):
+    """ABI v7: mmnas_mha_ln_* / mmnas_rel_mha_ln_* / mmnas_ffn_ln_* enqueue the SAME kernels with the SAME arguments
+    as the primitive entry points called one by one (functional.AttBlockPyFn / FFNBlockPyFn): with dropout ON and the
+    same rng state, outputs are bit-identical and gradients agree to accumulation-order noise."""
+    import mmnas_b200
+    from mmnas_b200 import runtime
+    from mmnas_b200.model.modules import RelGeometry
+    b, h = 4, 256
+    x, y, g4, xm, ym, gout = seeded_case(b, nx, ny, h, seed=11)
+    torch.manual_seed(5)
+    op = build(name, h, p=0.1).train()
+    lin = torch.nn.Linear(4, 64).to(DEV)
+    res = {}
+    for tag, flag in (('c', False), ('py', True)):
+        op.zero_grad()
+        lin.zero_grad()
+        for m in op.modules():                       # same per-call dropout salt in both runs
+            if hasattr(m, '_calls'):
+                m._calls = 0
+        mmnas_b200.manual_seed(77)
+        runtime.compose_in_python = flag
+        try:
+            out, gx, gy, _ = run_ours(op, mode, x, y, xm, ym, RelGeometry(g4.to(DEV), lin), gout)
+        finally:
+            runtime.compose_in_python = False
+        res[tag] = (out.detach().clone(), gx.clone(), None if gy is None else gy.clone(),
+                    {n_: p_.grad.clone() for n_, p_ in list(op.named_parameters()) + list(lin.named_parameters())
+                     if p_.grad is not None})
+    assert torch.equal(res['c'][0], res['py'][0])
+    assert normwise(res['c'][1], res['py'][1]) < 1e-5
+    if res['py'][2] is not None:
+        assert normwise(res['c'][2], res['py'][2]) < 1e-5
+    assert set(res['c'][3]) == set(res['py'][3])
+    for n_, g in res['py'][3].items():
+        assert normwise(res['c'][3][n_], g) < 1e-4, n_

@@ -561,3 +561,69 @@ def test_search_step_matches_oracle_at_baseline_config(mode):
     geno_ref = {'enc': [[O.ENC_SAFE[int(a.argmax())]] for a in ref_alphas[:12]],
                 'dec': [[O.DEC_SAFE[int(a.argmax())]] for a in ref_alphas[12:]]}
     assert net.genotype() == geno_ref                # identical argmax-selected architecture, both arms
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_search_executor_equals_the_module_path(mode):
+    """engine.SearchStep runs the supernet backbone through executor.SearchExecutor (static per-candidate plans, one
+    autograd node).  With the same seed, data and dropout state it must reproduce the per-module path (MixedOp ->
+    candidate blocks as separate autograd nodes): same sampled path, same loss, same gradients for the weight step
+    and the 'full' architecture step, and the same batched alpha_prob rule."""
+    import copy
+    import mmnas_b200
+    from mmnas_b200.engine import SearchStep
+    from mmnas_b200.model.nets import Net_Search
+    torch.manual_seed(888)
+    spec, cfg, init, inputs, target = _search_setup(8, p=0.1)
+    net_a = Net_Search(cfg, init).to(DEV).train()
+    net_b = copy.deepcopy(net_a)
+    din, dt = tuple(t.to(DEV) for t in inputs), target.to(DEV)
+    res = {}
+    with mmnas_b200.precision(mode):
+        for tag, net, use in (('executor', net_a, True), ('modules', net_b, False)):
+            step = SearchStep(net, use_executor=use)
+            assert (step.executor is not None) == use
+            for m in net.modules():
+                if hasattr(m, '_calls'):
+                    m._calls = 0                     # the module path salts dropout by call count: first call = 1
+            mmnas_b200.manual_seed(5)
+            torch.manual_seed(888)
+            lw = step.weight_step(din, dt)
+            gw = step.grads.flat.clone()
+            picks_w = [m.active_index[0] for m in net.redundant_modules]
+            for m in net.modules():
+                if hasattr(m, '_calls'):
+                    m._calls = 0
+            la = step.arch_step(din, dt)
+            ga = step.grads.flat.clone()
+            picks_a = [m.active_index[0] for m in net.redundant_modules]
+            alphas = torch.cat([p.detach().reshape(-1) for p in net.alpha_prob_parameters()])
+            res[tag] = (float(lw), gw, picks_w, float(la), ga, picks_a, alphas)
+    e, m = res['executor'], res['modules']
+    assert e[2] == m[2] and e[5] == m[5]
+    assert abs(e[0] - m[0]) <= 1e-6 * abs(m[0]) and abs(e[3] - m[3]) <= 2e-5 * abs(m[3])
+    assert normwise(e[1], m[1]) < 1e-5                         # weight-step gradients (flat buffer, every parameter)
+    assert normwise(e[4], m[4]) < (1e-4 if mode == 'fp32' else 2e-3)      # arch step: weights moved by one Adam step first
+    assert torch.allclose(e[6], m[6], atol=1e-3)
+
+
+def test_batched_sampling_on_cuda_draws_what_per_module_binarize_draws():
+    """The CUDA generator twin of tests/test_host_logic.py: one exponential_ per node + batched argmax reproduces
+    torch.multinomial's picks (the reference's MixedOp.binarize) under the same seed."""
+    from mmnas_b200.model.nets import Net_Search
+    torch.manual_seed(888)
+    spec, cfg, init, inputs, target = _search_setup(2)
+    net = Net_Search(cfg, init).to(DEV)
+    with torch.no_grad():
+        for p in net.alpha_prob_parameters():
+            p.add_(0.5 * torch.randn_like(p))
+    draws = {}
+    for batched in (False, True):
+        torch.manual_seed(888)
+        seq = []
+        for _ in range(6):
+            net.reset_binary_gates(batched=batched)
+            seq.append([m.active_index[0] for m in net.redundant_modules])
+        draws[batched] = seq
+    assert draws[True] == draws[False]
+    assert len({tuple(s) for s in draws[True]}) > 1
