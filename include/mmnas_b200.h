@@ -109,6 +109,14 @@ int mmnas_colsum(int dtype, const void* x, int rows, int cols, long ld, float* o
 /* ---- stem: bf16 copy of the region features (optional, NULL to skip) + make_mask() (full_vqa.py:113-114):
  * mask[r] = 1 iff every element of row r is zero (== sum|x| == 0). */
 int mmnas_cast_rowmask(const float* x, void* x_bf16, unsigned char* mask, int rows, int cols, mmnas_stream stream);
+/* the mask alone, for region features that arrive as bf16 already (a loader that stores them so halves the host->device bytes) */
+int mmnas_rowmask_bf16(const void* x_bf16, unsigned char* mask, int rows, int cols, mmnas_stream stream);
+
+/* ---- geometry producer: relation_embedding (mmnas/loader/load_data_vqa.py:7-33, twins in load_data_vgd.py:7-33 and
+ * load_data_itm.py:5-31) and the zero padding of load_data_vqa.py:236-239, on the device.  boxes [B,N,4] fp32
+ * (x1,y1,x2,y2), pad_mask [B,N] bytes (1 = padded region; NULL = all valid) -> g4 [B,N,N,4]: log-geometry of every
+ * valid pair, zeros elsewhere.  Lets a loader ship boxes instead of the N x N x 4 tensor. */
+int mmnas_box_geometry(const float* boxes, const unsigned char* pad_mask, float* g4, int B, int N, mmnas_stream stream);
 
 /* ---- optimizer tail: clip_grad_norm_ (train_vqa.py:310) + Adam (train_vqa.py:311 via optimizer.py:14-20) ------
  * out[0] = sum(x^2) over a flat fp32 buffer (n % 4 == 0).  Bit-reproducible (fixed summation order, no float

@@ -38,6 +38,8 @@ SIGNATURES = {
     'mmnas_sumsq_f32': [c_p, c_l, c_p, c_p, c_p],
     'mmnas_clip_adam': [c_p, c_i, c_p, c_p, c_p, c_f, c_f, c_f, c_f, c_p],
     'mmnas_rng_advance': [c_p, c_p],
+    'mmnas_rowmask_bf16': [c_p, c_p, c_i, c_i, c_p],
+    'mmnas_box_geometry': [c_p, c_p, c_p, c_i, c_i, c_p],
 }
 
 

@@ -186,6 +186,51 @@ __global__ void __launch_bounds__(EW_THREADS) cast_rowmask_kernel(const float* _
   if (threadIdx.x == 0) mask[blockIdx.x] = any_nz ? 0 : 1;
 }
 
+// make_mask() over a tensor that is already bf16 (a loader that ships bf16 region features): mask[r] = 1 iff row r is all zero
+__global__ void __launch_bounds__(EW_THREADS) rowmask_bf16_kernel(const uint2* __restrict__ x, unsigned char* __restrict__ mask, int cols) {
+  __shared__ int any_nz;
+  pdl_wait(); pdl_launch();
+  if (threadIdx.x == 0) any_nz = 0;
+  __syncthreads();
+  const uint2* row = x + (size_t)blockIdx.x * (cols >> 2);
+  bool nz = false;
+  for (int v = threadIdx.x; v < (cols >> 2); v += EW_THREADS) {
+    const uint2 w = row[v];
+    nz |= ((w.x | w.y) & 0x7FFF7FFFu) != 0u;          // +0 / -0 both count as zero, as in sum(|x|) == 0
+  }
+  if (__any_sync(0xffffffffu, nz) && (threadIdx.x & 31) == 0) atomicOr(&any_nz, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) mask[blockIdx.x] = any_nz ? 0 : 1;
+}
+
+// ---- geometry producer: the per-sample CPU step of the reference loader on the device ------------
+// relation_embedding (load_data_vqa.py:7-33) + the zero padding of :236-239: for valid boxes i, j
+//   g = (log max(|cx_i - cx_j| / w_i, 1e-3), log max(|cy_i - cy_j| / h_i, 1e-3), log(w_i / w_j), log(h_i / h_j)),
+// w = x2 - x1 + 1, h = y2 - y1 + 1, c = (min + max) / 2; pairs that involve a padded region are all-zero.  float32
+// arithmetic in the reference's operation order (IEEE divide, logf <= 1 ulp): the batch ships [B,N,4] boxes instead of
+// the [B,N,N,4] tensor (10 MB per 64 samples less host->device traffic).
+__global__ void __launch_bounds__(EW_THREADS) box_geometry_kernel(const float4* __restrict__ boxes, const unsigned char* __restrict__ pad,
+                                                                  float4* __restrict__ g4, int N) {
+  pdl_wait(); pdl_launch();
+  const int b = blockIdx.y;
+  const int nn = N * N;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nn; e += gridDim.x * blockDim.x) {
+    const int i = e / N, j = e - i * N;
+    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool valid = !pad || (pad[(size_t)b * N + i] == 0 && pad[(size_t)b * N + j] == 0);
+    if (valid) {
+      const float4 bi = __ldg(boxes + (size_t)b * N + i), bj = __ldg(boxes + (size_t)b * N + j);
+      const float cxi = (bi.x + bi.z) * 0.5f, cyi = (bi.y + bi.w) * 0.5f, wi = (bi.z - bi.x) + 1.f, hi = (bi.w - bi.y) + 1.f;
+      const float cxj = (bj.x + bj.z) * 0.5f, cyj = (bj.y + bj.w) * 0.5f, wj = (bj.z - bj.x) + 1.f, hj = (bj.w - bj.y) + 1.f;
+      out.x = logf(fmaxf(fabsf(__fdiv_rn(cxi - cxj, wi)), 1e-3f));
+      out.y = logf(fmaxf(fabsf(__fdiv_rn(cyi - cyj, hi)), 1e-3f));
+      out.z = logf(__fdiv_rn(wi, wj));
+      out.w = logf(__fdiv_rn(hi, hj));
+    }
+    g4[(size_t)b * nn + e] = out;
+  }
+}
+
 // ---- optimizer tail: clip_grad_norm_ + Adam in two passes over flat / tabled buffers ----------
 // Deterministic: every block stores its partial, the last block to finish adds them in block order.  (An atomicAdd
 // into one float would make the clip coefficient depend on block scheduling, and data-parallel replicas that apply
@@ -349,6 +394,24 @@ extern "C" int mmnas_cast_rowmask(const float* x, void* x_bf16, unsigned char* m
   if (rows == 0) return MMNAS_OK;
   MMNAS_CHECK_ARG(x && mask && ((uintptr_t)x % 16) == 0 && ((uintptr_t)x_bf16 % 8) == 0, "cast_rowmask: null / misaligned buffer");
   MMNAS_CUDA(mmnas_launch(cast_rowmask_kernel, dim3(rows), dim3(EW_THREADS), 0, (cudaStream_t)stream, x, (__nv_bfloat16*)x_bf16, mask, cols));
+  return MMNAS_OK;
+}
+
+extern "C" int mmnas_rowmask_bf16(const void* x_bf16, unsigned char* mask, int rows, int cols, mmnas_stream stream) {
+  MMNAS_CHECK_ARG(rows >= 0 && cols > 0 && (cols % 4) == 0, "rowmask_bf16: cols must be a multiple of 4");
+  if (rows == 0) return MMNAS_OK;
+  MMNAS_CHECK_ARG(x_bf16 && mask && ((uintptr_t)x_bf16 % 8) == 0, "rowmask_bf16: null / misaligned buffer");
+  MMNAS_CUDA(mmnas_launch(rowmask_bf16_kernel, dim3(rows), dim3(EW_THREADS), 0, (cudaStream_t)stream, (const uint2*)x_bf16, mask, cols));
+  return MMNAS_OK;
+}
+
+extern "C" int mmnas_box_geometry(const float* boxes, const unsigned char* pad_mask, float* g4, int B, int N, mmnas_stream stream) {
+  MMNAS_CHECK_ARG(B >= 0 && N >= 1, "box_geometry: bad sizes");
+  if (B == 0) return MMNAS_OK;
+  MMNAS_CHECK_ARG(boxes && g4 && ((uintptr_t)boxes % 16) == 0 && ((uintptr_t)g4 % 16) == 0, "box_geometry: null / misaligned buffer");
+  const int gx = ceil_div(N * N, EW_THREADS);
+  MMNAS_CUDA(mmnas_launch(box_geometry_kernel, dim3(gx, B), dim3(EW_THREADS), 0, (cudaStream_t)stream, (const float4*)boxes, pad_mask,
+                          (float4*)g4, N));
   return MMNAS_OK;
 }
 

@@ -734,13 +734,20 @@ class StemImageFn(Function):
         mask = torch.empty((B, N), dtype=torch.uint8, device=dev)
         y = _empty((B, N, H), torch.float32, dev)
         feat16 = None
+        if feat.dtype == torch.bfloat16:     # compact loader format: the features arrive as bf16 (what the bf16 arm
+            feat16 = feat.view(M, Fin)       # casts them to anyway), only the mask is left to compute
+            K.rowmask_bf16(feat16, mask, M, Fin)
+            if not bf:
+                feat = feat.float()
         if bf:
-            feat16 = _empty((M, Fin), torch.bfloat16, dev)
-            K.cast_rowmask(feat, feat16, mask, M, Fin)
+            if feat16 is None:
+                feat16 = _empty((M, Fin), torch.bfloat16, dev)
+                K.cast_rowmask(feat, feat16, mask, M, Fin)
             w16 = K.cast_bf16(W.detach())
             K.gemm_bf16(M, H, Fin, feat16, Fin, 0, w16, Fin, 0, y, H, bias=b)
         else:
-            K.cast_rowmask(feat, None, mask, M, Fin)
+            if feat16 is None:
+                K.cast_rowmask(feat, None, mask, M, Fin)
             K.gemm_f32(M, H, Fin, feat, Fin, 1, W, 1, Fin, y, H, bias=b)
         ctx.bf, ctx.dims = bf, (M, Fin, H)
         ctx.params = (W, b)

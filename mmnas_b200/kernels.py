@@ -130,3 +130,15 @@ def clip_adam(table, n_chunks, sumsq_buf, lr, step_state, beta1, beta2, eps, max
 
 def rng_advance(state):
     call('mmnas_rng_advance', ptr(state), stream())
+
+
+def box_geometry(boxes, pad_mask):
+    """boxes [B,N,4] fp32, pad_mask uint8 [B,N] (1 = padded) or None -> g4 [B,N,N,4] (load_data_vqa.py:7-33,236-239)."""
+    B, N = boxes.shape[0], boxes.shape[1]
+    g4 = torch.empty((B, N, N, 4), dtype=torch.float32, device=boxes.device)
+    call('mmnas_box_geometry', ptr(boxes), ptr(pad_mask), ptr(g4), B, N, stream())
+    return g4
+
+
+def rowmask_bf16(x16, mask, rows, cols):
+    call('mmnas_rowmask_bf16', ptr(x16), ptr(mask), rows, cols, stream())

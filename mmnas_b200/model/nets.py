@@ -134,6 +134,14 @@ class _NetBase(nn.Module):
                                              runtime.get_precision())
         # x_rel is never consumed (no relation op is an encoder candidate); the reference still embeds it in
         # Net_Search (hygr_vqa.py:130) — the parameters exist here for checkpoint parity, the dead matmul does not run.
+        if y_rel.dim() == 3:
+            # compact loader format: raw boxes [B,N,4] instead of the [B,N,N,4] log-geometry the
+            # reference's DataLoader computes per sample on the CPU (load_data_vqa.py:7-33,236-239) — built here
+            from .. import kernels as K
+            from .._lib import require_cuda
+            require_cuda(y_rel)
+            pad = y_mask.reshape(y_mask.shape[0], -1).contiguous().view(torch.uint8)
+            y_rel = K.box_geometry(y_rel.contiguous().float(), pad)
         ex = getattr(self, '_executor', None)
         if ex is not None and ex.usable(self.rel_mode):
             # engine search step: the whole supernet backbone is one autograd node over static per-candidate plans
@@ -162,6 +170,55 @@ class _NetBase(nn.Module):
         return out
 
     make_mask = staticmethod(make_mask)
+
+    # ---- ITM hard-negative mining / retrieval scoring ----------------------------------------------
+    @torch.no_grad()
+    def score_pairs(self, images, captions, img_index, cap_index):
+        """Matching scores of the pairs (images[img_index[p]], captions[cap_index[p]]) in inference mode, what
+        train_itm.py:307-320 / :340-353 (hard-negative mining: NEG_BATCHSIZE x NEG_RANDSIZE = 50 x 64 = 3 200 pairs per
+        forward) and :476-500 (retrieval evaluation) compute with `net(input)` on inputs where one side is REPEATED
+        64 times.  Here every unique image and caption is encoded once:
+          * captions: embedding, LSTM and the whole encoder (it never sees the image) run on the unique captions;
+          * images: the stem projection, the padding mask, the pairwise geometry and the decoder blocks that precede
+            the first GuidedAtt block run on the unique images;
+        then both sides are gathered to the pair list and the rest of the decoder + the head run on the pairs.  Same
+        result as `self(expanded inputs)` (tests/test_gpu_nets.py), with the repeated side's work divided by the
+        repetition count.  images = (frcn_feat [U,N,F], bbox_feat, rel_img [U,N,N,4] or boxes [U,N,4]); captions =
+        (cap_ix [V,T], rel_cap); img_index / cap_index: int64 [P] on the same device."""
+        frcn_feat, bbox_feat, y_rel = images
+        cap_ix, x_rel = captions
+        x_mask_u = make_mask(cap_ix.unsqueeze(2))
+        x_u, _ = self.lstm(self.embedding(cap_ix))
+        y_u, y_mask_u = StemImageFn.apply(frcn_feat, self.imgfeat_linear.weight, self.imgfeat_linear.bias,
+                                          runtime.get_precision())
+        if y_rel.dim() == 3:
+            from .. import kernels as K
+            y_rel = K.box_geometry(y_rel.contiguous().float(), y_mask_u.reshape(y_mask_u.shape[0], -1).contiguous().view(torch.uint8))
+        geo_u = RelGeometry(y_rel, self.linear_y_rel) if self.rel_mode == 'geometry' else F.relu(self.linear_y_rel(y_rel))
+        for cell in self.backnone.cells_enc:
+            x_u = cell(s=x_u, s_mask=x_mask_u, rel_embed=x_rel)
+        rows = [ops for cell in self.backnone.cells_dec for ops in cell.dag]
+        from .modules import GuidedAtt
+        n_free = 0                               # leading decoder nodes that do not read the encoder output
+        while n_free < len(rows) and not any(isinstance(op, (GuidedAtt, MixedOp)) for op in rows[n_free]):
+            n_free += 1
+        y_u = _chain(rows[:n_free], y_u, None, y_mask_u, None, geo_u)
+        x, x_mask = x_u[cap_index], x_mask_u[cap_index]
+        y, y_mask = y_u[img_index], y_mask_u[img_index]
+        if isinstance(geo_u, RelGeometry):
+            geo = RelGeometry(geo_u.g4[img_index], self.linear_y_rel)
+        else:
+            geo = geo_u[img_index]
+        y = _chain(rows[n_free:], y, x, y_mask, x_mask, geo)
+        return self.head(x, y, x_mask, y_mask)
+
+    @staticmethod
+    def hard_negatives(scores, neg_idx_list, group, k):
+        """train_itm.py:316-320: per anchor, the k highest-scoring of its `group` random negatives."""
+        scores = scores.view(-1, group)
+        top = torch.argsort(scores, dim=-1, descending=True)[:, :k]
+        rows = torch.arange(top.size(0), device=top.device).unsqueeze(1).expand_as(top)
+        return neg_idx_list.to(top.device)[rows, top]
 
 
 class Net_Full(_NetBase):

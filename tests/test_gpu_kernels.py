@@ -529,3 +529,25 @@ def test_gemm_bf16_random_sweep():
                 os.environ.pop(var, None)
             else:
                 os.environ[var] = val
+
+
+def test_box_geometry_matches_reference_golden():
+    """mmnas_box_geometry vs relation_embedding of the unmodified reference (load_data_vqa.py:7-33; golden geometry.npz,
+    incl. two identical boxes that hit the 1e-3 clamp) and the loader's zero padding (:236-239)."""
+    from mmnas_b200 import kernels as K
+    from tests.util import load_golden
+    r = load_golden('geometry.npz')
+    boxes, rel = r['boxes'], r['rel']
+    n = boxes.shape[0]
+    g = K.box_geometry(boxes.view(1, n, 4).to(DEV), None)
+    assert normwise(g[0], rel) < 2e-6
+    N = 12                                                     # padded to 12 regions, two samples, ragged
+    bx = torch.zeros(2, N, 4)
+    bx[0, :n], bx[1, :5] = boxes, boxes[:5]
+    pad = torch.ones(2, N, dtype=torch.uint8)
+    pad[0, :n], pad[1, :5] = 0, 0
+    g = K.box_geometry(bx.to(DEV), pad.to(DEV)).cpu()
+    ref = torch.zeros(2, N, N, 4)
+    ref[0, :n, :n], ref[1, :5, :5] = rel, rel[:5, :5]
+    assert normwise(g, ref) < 2e-6
+    assert torch.equal(g[0, n:], ref[0, n:]) and torch.equal(g[1, :, 5:], ref[1, :, 5:])      # padding exactly zero

@@ -627,3 +627,76 @@ def test_batched_sampling_on_cuda_draws_what_per_module_binarize_draws():
         draws[batched] = seq
     assert draws[True] == draws[False]
     assert len({tuple(s) for s in draws[True]}) > 1
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_compact_input_format_equals_the_loader_format(mode):
+    """a batch that ships bf16 region features and raw boxes [B,N,4] gives the same step as the
+    reference loader's format (fp32 features + the [B,N,N,4] geometry computed on the CPU, load_data_vqa.py:7-33):
+    the geometry is rebuilt on the device, the features are what the bf16 arm casts them to anyway."""
+    import mmnas_b200
+    from mmnas_b200.data.synthetic import compact, make_batch
+    from mmnas_b200.model.nets import Net_Full
+    torch.manual_seed(888)
+    spec, cfg, init, _, _ = full_setup(4)
+    batch = make_batch(spec, 888)
+    if mode == 'fp32':                                          # make the fp32 features bf16-representable: same inputs
+        batch = ((batch[0][0].to(torch.bfloat16).float(),) + batch[0][1:], batch[1])
+        batch[0][2]._boxes = make_batch(spec, 888)[0][2]._boxes
+    net = Net_Full(cfg, init).train()
+    with torch.no_grad():       # the device logf differs from the host log by <= 1 ulp: compare where the geometry path is
+        condition_rsa_(dict(net.named_parameters()))      # well-conditioned (tests/util.py condition_rsa_)
+    net = net.to(DEV)
+    res = []
+    for b in (batch, compact(batch)):
+        net.zero_grad()
+        inputs, target = b
+        with mmnas_b200.precision(mode):
+            pred = net(tuple(t.to(DEV) for t in inputs))
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(pred, target.to(DEV), reduction='sum')
+            loss.backward()
+        res.append((pred.detach().clone(), {n_: p_.grad.clone() for n_, p_ in net.named_parameters()}))
+    (pa, ga), (pb, gb) = res
+    assert res[1][0].shape == pa.shape
+    assert normwise(pb, pa) < (2e-6 if mode == 'fp32' else 2e-3)
+    gmax = max(float(g.abs().max()) for g in ga.values())
+    for n_, g in ga.items():
+        assert normwise(gb[n_], g, 1e-2 * gmax) < (2e-5 if mode == 'fp32' else 2e-2), n_
+
+
+@pytest.mark.parametrize('repeated', ['image', 'caption'])
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_itm_mining_forward_equals_the_expanded_forward(mode, repeated):
+    """SURVEY §8f row 4 (train_itm.py:299-363): scoring 6 anchors x 8 random negatives.  The reference expands the
+    repeated side 8x and calls net(input) in eval mode; score_pairs() encodes every unique image / caption once.
+    Same scores, same hard negatives."""
+    import mmnas_b200
+    from mmnas_b200 import genotypes
+    from mmnas_b200.data.synthetic import Cfg, make_batch, init_dict, spec_for
+    from mmnas_b200.model.nets import Net_Full
+    torch.manual_seed(888)
+    n_anchor, group = 6, 8
+    spec = spec_for('itm', batch=n_anchor * group // 3, vocab=1000, n_ans=10)     # make_batch stacks 3 x batch rows
+    cfg = Cfg(genotype=genotypes.shipped('mmnas_itm'), DROPOUT_R=0.1)
+    (frcn, bbox, rel, caps, rel_cap), _ = make_batch(spec, seed=5)
+    P = n_anchor * group
+    frcn, bbox, rel, caps, rel_cap = (t[:P].to(DEV) for t in (frcn, bbox, rel, caps, rel_cap))
+    net = Net_Full(cfg, init_dict(spec), task='itm').to(DEV).eval()
+    g = torch.Generator().manual_seed(1)
+    anchor = torch.arange(n_anchor).repeat_interleave(group).to(DEV)              # the repeated side: 0,0,..,1,1,..
+    other = torch.randperm(P, generator=g).to(DEV)                                  # the distinct side
+    if repeated == 'image':
+        img_index, cap_index = anchor, other
+        images, captions = (frcn[:n_anchor], bbox[:n_anchor], rel[:n_anchor]), (caps, rel_cap)
+    else:
+        img_index, cap_index = other, anchor
+        images, captions = (frcn, bbox, rel), (caps[:n_anchor], rel_cap[:n_anchor])
+    with mmnas_b200.precision(mode), torch.no_grad():
+        expanded = (images[0][img_index], images[1][img_index], images[2][img_index], captions[0][cap_index],
+                    captions[1][cap_index])
+        ref = net(expanded)                                                         # what the reference's loop evaluates
+        got = net.score_pairs(images, captions, img_index, cap_index)
+    assert got.shape == ref.shape == (P,)
+    assert normwise(got, ref) < (1e-6 if mode == 'fp32' else 1e-5)
+    neg_idx = torch.randint(0, 10 ** 4, (n_anchor, group), generator=g)
+    assert torch.equal(net.hard_negatives(got, neg_idx, group, 5), net.hard_negatives(ref, neg_idx, group, 5))
