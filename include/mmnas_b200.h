@@ -50,6 +50,18 @@ int mmnas_gemm_bf16(int M, int N, int K, const void* A, long lda, int a_mn_major
                     const void* aux, long ld_aux, float aux_scale, int split_k, const unsigned long long* rng_state,
                     unsigned long long salt, float p, mmnas_stream stream);
 
+/* bf16 arm, projection with the block tail fused into its epilogue (tcgen05 cta_group::2 pairs in a cluster that owns
+ * whole rows; row statistics across the cluster through distributed shared memory):
+ *   z = x + dropout(A W^T + bias) ; out = gamma (z - mean) / (std_unbiased + eps) + beta        (modules.py:261-271, :52-56)
+ * A [M,K] bf16 (pitch lda), W [N,K] bf16 (pitch ldb), bias [N] or NULL, x [M,N] fp32 residual input or NULL; writes z [M,N]
+ * fp32 (saved for the backward), out [M,N] fp32, out_bf16 [M,N], mean / sigma [M].  N must be 256 or 512 and gamma, beta,
+ * out_bf16 non-NULL; otherwise returns MMNAS_ERR_UNSUPPORTED (-2) and the caller runs mmnas_gemm_bf16 +
+ * mmnas_ln_residual_fwd.  Dropout stream identical to mmnas_ln_residual_fwd's. */
+int mmnas_gemm_ln_bf16(int M, int N, int K, const void* A, long lda, const void* W, long ldb, const float* bias,
+                       const float* x, const float* gamma, const float* beta, float eps, float* z, float* out,
+                       void* out_bf16, float* mean, float* sigma, const unsigned long long* rng_state,
+                       unsigned long long salt, float p, mmnas_stream stream);
+
 /* ---- attention core: MHAtt.att (modules.py:190-199) / RelMHAtt.forward (:232-240) ---------------------
  * q [B*Nq rows, pitch ldq], k/v [B*Nk rows]; head h reads columns [h*64, h*64+64).  kmask [B,Nk] bytes, 1 = padded
  * key (masked_fill(mask, -1e9) AFTER the bias add); bias [B,heads,Nq,Nk] fp32 or NULL; o [B*Nq rows, pitch ldo]

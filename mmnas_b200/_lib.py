@@ -21,6 +21,7 @@ SIGNATURES = {
                        c_f, c_p],
     'mmnas_gemm_bf16': [c_i, c_i, c_i, c_p, c_l, c_i, c_p, c_l, c_i, c_p, c_l, c_i, c_p, c_i, c_i, c_p, c_l, c_f, c_i,
                         c_p, c_u64, c_f, c_p],
+    'mmnas_gemm_ln_bf16': [c_i, c_i, c_i, c_p, c_l, c_p, c_l, c_p, c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_p, c_p, c_p, c_u64, c_f, c_p],
     'mmnas_attn_fwd': [c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_l, c_p, c_l, c_p, c_l, c_p, c_p, c_p, c_l, c_f, c_p, c_u64,
                        c_f, c_p],
     'mmnas_attn_bwd': [c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_l, c_p, c_l, c_p, c_l, c_p, c_p, c_p, c_l, c_p, c_l, c_p,

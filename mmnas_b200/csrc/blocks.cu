@@ -9,6 +9,7 @@
 // lets the weight-gradient GEMMs fill SMs the dgrad / attention chain leaves idle.  A block forward or backward is then
 // ONE foreign call instead of 5-9 (forward) / 9-14 (backward), which is what bounds the eager search step.
 #include <atomic>
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/mmnas_b200.h"
 
@@ -21,6 +22,33 @@ namespace {
   } while (0)
 
 constexpr int HEAD = 64;
+
+// Fused projection + residual + LayerNorm (gemm_ln.cu) wherever it applies; MMNAS_FUSE_LN=0 keeps the two-kernel tail
+// (A/B measurements only).
+bool fuse_ln() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("MMNAS_FUSE_LN"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on == 1;
+}
+
+// branch GEMM + block tail: z = x + dropout(A W^T + bias), out = LN(z).  One launch when the fused kernel takes the
+// shape, else the projection into z followed by the residual / LayerNorm kernel.
+int tail16(int M, int H, int K, const void* A, const void* w16, const float* bias, const float* x, const float* ln_a,
+           const float* ln_b, float eps, float* z, float* out, void* out16, float* mean, float* sigma,
+           const unsigned long long* rng, unsigned long long salt, float p, mmnas_stream s) {
+  // The fused kernel owns a 256-row block per cluster (2 CTAs at H = 256, 4 at H = 512) and runs one block per cluster:
+  // it wins when the row blocks fill most of one wave of clusters (measured on B200, scripts/bench_gemm_ln.py:
+  // 6400 x 512 x 512 17.1 vs 21.2 us, 6400 x 512 x 2048 25.5 vs 30.1 us) and loses on the short text stream (896 rows:
+  // 13.7 vs 11.1 us, its epilogue is not overlapped with anything) or when the blocks spill into a second wave.
+  const int row_blocks = (M + 255) / 256, per_wave = H == 256 ? 74 : 37;       // clusters of 2 / 4 CTAs on 148 SMs
+  if (fuse_ln() && ln_a && out16 && (H == 256 || H == 512) && row_blocks <= per_wave && 2 * row_blocks > per_wave) {
+    const int rc = mmnas_gemm_ln_bf16(M, H, K, A, K, w16, K, bias, x, ln_a, ln_b, eps, z, out, out16, mean, sigma, rng, salt, p, s);
+    if (rc != MMNAS_ERR_UNSUPPORTED) return rc;
+  }
+  int rc = mmnas_gemm_bf16(M, H, K, A, K, 0, w16, K, 0, z, H, 0, bias, 0, 0, nullptr, 0, 1.f, 1, nullptr, 0, 0.f, s);
+  if (rc != MMNAS_OK) return rc;
+  return mmnas_ln_residual_fwd(M, H, x, z, ln_a, ln_b, eps, out, out16, mean, sigma, rng, salt, p, s);
+}
 
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
@@ -248,10 +276,13 @@ int att_fwd(const mmnas_att_block* d, bool rel) {
                     d->p_att > 0.f ? rng : nullptr, d->salt_att, d->p_att, s));
   // --- merge projection, residual, LayerNorm (z = x + dropout(branch) overwrites the branch buffer)
   float* z = (float*)(ws + L.z);
-  if (bf) RC(gemm16(Mq, H, I, atted, I, 0, d->w16_m, I, 0, z, H, 0, nullptr, 0, 0, 1, s));
-  else RC(gemm32(Mq, H, I, (const float*)atted, I, 1, d->Wm, 1, I, z, H, nullptr, 0, 0, s));
+  const unsigned long long* rng_out = d->p_out > 0.f ? rng : nullptr;
+  if (bf)
+    return tail16(Mq, H, I, atted, d->w16_m, nullptr, d->residual ? d->x : nullptr, d->ln_a, d->ln_b, d->eps, z, d->out, d->out16,
+                  (float*)(ws + L.mean), (float*)(ws + L.sigma), rng_out, d->salt_out, d->p_out, s);
+  RC(gemm32(Mq, H, I, (const float*)atted, I, 1, d->Wm, 1, I, z, H, nullptr, 0, 0, s));
   RC(mmnas_ln_residual_fwd(Mq, H, d->residual ? d->x : nullptr, z, d->ln_a, d->ln_b, d->eps, d->out, d->out16,
-                           (float*)(ws + L.mean), (float*)(ws + L.sigma), d->p_out > 0.f ? rng : nullptr, d->salt_out, d->p_out, s));
+                           (float*)(ws + L.mean), (float*)(ws + L.sigma), rng_out, d->salt_out, d->p_out, s));
   return MMNAS_OK;
 }
 
@@ -427,12 +458,12 @@ int ffn_fwd(const mmnas_ffn_block* d) {
     // bias, ReLU and the hidden dropout run in the epilogue of the first GEMM; the second adds its bias
     RC(gemm16(M, F, H, x16, H, 0, d->w16_1, H, 0, h, F, 1, d->b1, 1, 0, 1, s, nullptr, 0, 1.f, drop_mid ? rng : nullptr,
               d->salt_mid, drop_mid ? d->p_mid : 0.f));
-    RC(gemm16(M, H, F, h, F, 0, d->w16_2, F, 0, z, H, 0, d->b2, 0, 0, 1, s));
-  } else {
-    RC(gemm32(M, F, H, d->x, H, 1, d->W1, 1, H, (float*)h, F, d->b1, drop_mid ? 2 : 1, 0, s, nullptr, 0, 1.f,
-              drop_mid ? rng : nullptr, d->salt_mid, drop_mid ? d->p_mid : 0.f));
-    RC(gemm32(M, H, F, (const float*)h, F, 1, d->W2, 1, F, z, H, d->b2, 0, 0, s));
+    return tail16(M, H, F, h, d->w16_2, d->b2, d->residual ? d->x : nullptr, d->ln_a, d->ln_b, d->eps, z, d->out, d->out16,
+                  (float*)(ws + L.mean), (float*)(ws + L.sigma), d->p_out > 0.f ? rng : nullptr, d->salt_out, d->p_out, s);
   }
+  RC(gemm32(M, F, H, d->x, H, 1, d->W1, 1, H, (float*)h, F, d->b1, drop_mid ? 2 : 1, 0, s, nullptr, 0, 1.f,
+            drop_mid ? rng : nullptr, d->salt_mid, drop_mid ? d->p_mid : 0.f));
+  RC(gemm32(M, H, F, (const float*)h, F, 1, d->W2, 1, F, z, H, d->b2, 0, 0, s));
   RC(mmnas_ln_residual_fwd(M, H, d->residual ? d->x : nullptr, z, d->ln_a, d->ln_b, d->eps, d->out, d->out16,
                            (float*)(ws + L.mean), (float*)(ws + L.sigma), d->p_out > 0.f ? rng : nullptr, d->salt_out, d->p_out, s));
   return MMNAS_OK;

@@ -142,3 +142,10 @@ def box_geometry(boxes, pad_mask):
 
 def rowmask_bf16(x16, mask, rows, cols):
     call('mmnas_rowmask_bf16', ptr(x16), ptr(mask), rows, cols, stream())
+
+
+def gemm_ln_bf16(M, N, K, A, lda, W, ldb, bias, x, gamma, beta, eps, z, out, out16, mean, sigma, drop=NO_DROP):
+    """Fused projection + residual + LayerNorm (bf16 arm).  Raises MMnasLibraryError(-2) for unsupported shapes."""
+    st, salt, p = drop.args()
+    call('mmnas_gemm_ln_bf16', M, N, K, ptr(A), lda, ptr(W), ldb, ptr(bias), ptr(x), ptr(gamma), ptr(beta), eps, ptr(z), ptr(out),
+         ptr(out16), ptr(mean), ptr(sigma), st, salt, p, stream())

@@ -271,16 +271,22 @@ def test_mixed_op_two_mode_matches_reference_golden(mode):
 
 
 @pytest.mark.parametrize('mode', ['fp32', 'bf16'])
-@pytest.mark.parametrize('name,nx,ny', [('self_att_64', 100, 14), ('self_att_64', 14, 100), ('rel_self_att_64', 100, 14),
-                                        ('guided_att_64', 100, 14), ('guided_att_64', 36, 50), ('feed_forward', 100, 14)])
-def test_block_level_c_calls_equal_the_python_composition(name, nx, ny, mode):
+@pytest.mark.parametrize('name,nx,ny,b,h', [('self_att_64', 100, 14, 4, 256), ('self_att_64', 14, 100, 4, 256),
+                                            ('rel_self_att_64', 100, 14, 4, 256), ('guided_att_64', 100, 14, 4, 256),
+                                            ('guided_att_64', 36, 50, 4, 256), ('feed_forward', 100, 14, 4, 256),
+                                            # B = 64, H = 512: the bf16 arm takes the fused projection + LayerNorm kernel
+                                            ('self_att_64', 100, 14, 64, 512), ('guided_att_64', 100, 14, 64, 512),
+                                            ('feed_forward', 100, 14, 64, 512)])
+def test_block_level_c_calls_equal_the_python_composition(name, nx, ny, b, h, mode):
     """ABI v7: mmnas_mha_ln_* / mmnas_rel_mha_ln_* / mmnas_ffn_ln_* enqueue the SAME kernels with the SAME arguments
     as the primitive entry points called one by one (functional.AttBlockPyFn / FFNBlockPyFn): with dropout ON and the
-    same rng state, outputs are bit-identical and gradients agree to accumulation-order noise."""
+    same rng state, outputs are bit-identical (fp32 arm; the bf16 arm's fused projection + LayerNorm epilogue agrees to
+    summation-order noise) and gradients agree to accumulation-order noise."""
     import mmnas_b200
     from mmnas_b200 import runtime
     from mmnas_b200.model.modules import RelGeometry
-    b, h = 4, 256
+    if b == 64 and mode == 'fp32':
+        pytest.skip('the large case exists for the fused bf16 kernel')
     x, y, g4, xm, ym, gout = seeded_case(b, nx, ny, h, seed=11)
     torch.manual_seed(5)
     op = build(name, h, p=0.1).train()
@@ -301,10 +307,16 @@ def test_block_level_c_calls_equal_the_python_composition(name, nx, ny, mode):
         res[tag] = (out.detach().clone(), gx.clone(), None if gy is None else gy.clone(),
                     {n_: p_.grad.clone() for n_, p_ in list(op.named_parameters()) + list(lin.named_parameters())
                      if p_.grad is not None})
-    assert torch.equal(res['c'][0], res['py'][0])
-    assert normwise(res['c'][1], res['py'][1]) < 1e-5
+    if mode == 'fp32':
+        assert torch.equal(res['c'][0], res['py'][0])
+    else:       # the C path fuses residual + LayerNorm into the projection's epilogue (gemm_ln.cu): same arithmetic, other summation order
+        assert normwise(res['c'][0], res['py'][0]) < 5e-6
+    # fused tail: mean / sigma differ in the last bits, so a few elements of the bf16 branch gradient round the other
+    # way (one bf16 ulp) before they enter the backward GEMMs — 1e-4-level differences, far inside the bf16 gate
+    gtol = 1e-3 if (b == 64 and mode == 'bf16') else 1e-5
+    assert normwise(res['c'][1], res['py'][1]) < gtol
     if res['py'][2] is not None:
-        assert normwise(res['c'][2], res['py'][2]) < 1e-5
+        assert normwise(res['c'][2], res['py'][2]) < gtol
     assert set(res['c'][3]) == set(res['py'][3])
     for n_, g in res['py'][3].items():
-        assert normwise(res['c'][3][n_], g) < 1e-4, n_
+        assert normwise(res['c'][3][n_], g) < 10 * gtol, n_

@@ -551,3 +551,44 @@ def test_box_geometry_matches_reference_golden():
     ref[0, :n, :n], ref[1, :5, :5] = rel, rel[:5, :5]
     assert normwise(g, ref) < 2e-6
     assert torch.equal(g[0, n:], ref[0, n:]) and torch.equal(g[1, :, 5:], ref[1, :, 5:])      # padding exactly zero
+
+
+@pytest.mark.parametrize('M,N,K', [(6400, 512, 512), (6400, 512, 2048), (896, 512, 2048), (324, 512, 512), (6400, 256, 256),
+                                   (896, 256, 1024), (200, 256, 256)])
+@pytest.mark.parametrize('variant', ['plain', 'bias_residual_dropout'])
+def test_fused_gemm_layernorm_matches_the_two_kernel_tail(M, N, K, variant):
+    """mmnas_gemm_ln_bf16 (projection + residual + dropout + LayerNorm in one tcgen05 cluster kernel, row statistics over
+    distributed shared memory) against mmnas_gemm_bf16 followed by mmnas_ln_residual_fwd on the same operands: z, out,
+    its bf16 copy, mean and sigma; same dropout stream (identical masks)."""
+    from mmnas_b200 import kernels as K_
+    import mmnas_b200
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(DEV).to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV).to(torch.bfloat16)
+    gamma = (1 + 0.1 * torch.randn(N, generator=g)).to(DEV)
+    beta = (0.1 * torch.randn(N, generator=g)).to(DEV)
+    full = variant != 'plain'
+    bias = (0.5 * torch.randn(N, generator=g)).to(DEV) if full else None
+    x = (torch.randn(M, N, generator=g) + 0.3).to(DEV) if full else None
+    mmnas_b200.manual_seed(3)
+    drop = K_.Drop(mmnas_b200.runtime.rng_state(DEV), 12345, 0.1) if full else K_.NO_DROP
+    # reference: the two-kernel tail
+    z_ref = torch.empty(M, N, device=DEV)
+    K_.gemm_bf16(M, N, K, A, K, 0, W, K, 0, z_ref, N, bias=bias)
+    out_ref, out16_ref = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    mean_ref, sigma_ref = torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+    K_.ln_residual_fwd(M, N, x, z_ref, gamma, beta, 1e-6, out_ref, out16_ref, mean_ref, sigma_ref, drop)
+    # fused
+    z, out = torch.full((M, N), float('nan'), device=DEV), torch.full((M, N), float('nan'), device=DEV)
+    out16 = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    mean, sigma = torch.zeros(M, device=DEV), torch.zeros(M, device=DEV)
+    K_.gemm_ln_bf16(M, N, K, A, K, W, K, bias, x, gamma, beta, 1e-6, z, out, out16, mean, sigma, drop)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all() and torch.isfinite(z).all()
+    assert normwise(z, z_ref) < 1e-6
+    if full:
+        assert torch.equal(z == x, z_ref == x)                 # the same elements were dropped
+    assert normwise(mean, mean_ref, 1e-3) < 1e-5 and normwise(sigma, sigma_ref) < 1e-6
+    assert normwise(out, out_ref) < 2e-6
+    assert normwise(out16.float(), out16_ref.float()) < 8e-3   # one bf16 ulp where the fp32 values straddle a rounding boundary
+    assert (out16 != out16_ref).float().mean() < 1e-3
