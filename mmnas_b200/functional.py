@@ -778,6 +778,146 @@ class StemImageFn(Function):
 
 
 # ----------------------------------------------------------------------------------------------------------
+# callers' dense layers: the Linear(+ReLU+dropout) layers of AttFlat and of the task heads
+# (modules.py:13-41,59-85; full_vqa.py:105-109; full_vgd.py:105-112; full_itm.py:109-110) on the library GEMMs
+# ----------------------------------------------------------------------------------------------------------
+def _pad32(n):
+    return (n + 31) // 32 * 32
+
+
+class LinearFn(Function):
+    """y = dropout(relu(x W^T + b)) (ReLU / dropout optional) over the last dimension of x.
+
+    bf16 arm: tcgen05 GEMM with the bias / ReLU / dropout epilogue; backward = one masked cast, a column sum, a split-K
+    weight-gradient GEMM and a dgrad GEMM.  fp32 arm: the FFMA GEMM.  The tensor-core GEMM wants an output width that
+    is a multiple of 32: other widths (3129 answers, the 1- and 4-wide scoring layers) run on zero-padded weight rows
+    and a padded output pitch, and hand back the leading columns."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, relu, drop, precision):
+        require_cuda(x, W)
+        ctx.set_materialize_grads(False)
+        dev = x.device
+        N, Kin = W.shape
+        shape = x.shape
+        x2 = x.reshape(-1, Kin).contiguous()
+        M = x2.shape[0]
+        # the tensor-core GEMM needs every GEMM 'N' of forward / dgrad / wgrad to be a multiple of 32: the output width is
+        # padded, an input width that is not (toy configurations only) takes the FFMA GEMM
+        bf = precision == 'bf16' and Kin % 32 == 0
+        Np = _pad32(N) if bf else N
+        y = torch.empty((M, Np), dtype=torch.float32, device=dev)
+        if bf:
+            x16 = getattr(x, '_mmnas_bf16', None)
+            x16 = x16.reshape(M, Kin) if (x16 is not None and x16.numel() == x2.numel()) else K.cast_bf16(x2)
+            if Np == N:
+                w16, bp = K.cast_bf16(W.detach()), b
+            else:
+                w16 = torch.zeros((Np, Kin), dtype=torch.bfloat16, device=dev)
+                K.cast_bf16(W.detach(), w16[:N])
+                bp = None
+                if b is not None:
+                    bp = torch.zeros(Np, dtype=torch.float32, device=dev)
+                    bp[:N].copy_(b.detach())
+            K.gemm_bf16(M, Np, Kin, x16, Kin, 0, w16, Kin, 0, y, Np, bias=bp, relu=relu, drop=drop)
+            ctx.save_for_backward(x16, w16, y if relu else None)
+        else:
+            K.gemm_f32(M, N, Kin, x2, Kin, 1, W, 1, Kin, y, N, bias=b, epilogue=(2 if drop.active else 1) if relu else 0,
+                       drop=drop if relu else K.NO_DROP)
+            ctx.save_for_backward(x2, W, y if relu else None)
+        if drop.active and not relu:
+            raise NotImplementedError('dropout without ReLU is not used by any caller layer')
+        ctx.meta = (bf, M, N, Np, Kin, shape, relu, (1.0 / (1.0 - drop.p)) if drop.active else 1.0)
+        ctx.params = (W, b)
+        out = y[:, :N] if Np != N else y
+        return out.reshape(shape[:-1] + (N,))
+
+    @staticmethod
+    def backward(ctx, dy):
+        if dy is None:
+            return (None,) * 6
+        bf, M, N, Np, Kin, shape, relu, scale = ctx.meta
+        xs, ws, y = ctx.saved_tensors
+        W, b = ctx.params
+        dev = dy.device
+        dy2 = dy.reshape(M, N)
+        # gradient w.r.t. the pre-activation: the saved output is 0 exactly where ReLU or dropout cut the element
+        if relu:
+            dpre = dy2 * (y[:, :N] > 0)
+            if scale != 1.0:
+                dpre = dpre * scale
+        else:
+            dpre = dy2
+        sinks = _direct((W, b)) if b is not None else _direct((W,))
+        direct = sinks is not None
+        gW = sinks[0] if direct else torch.empty_like(W, dtype=torch.float32)
+        gb = None
+        if b is not None:
+            gb = sinks[1] if direct else torch.empty_like(b, dtype=torch.float32)
+        dx = torch.empty((M, Kin), dtype=torch.float32, device=dev)
+        if bf:
+            d16 = torch.zeros((M, Np), dtype=torch.bfloat16, device=dev) if Np != N else torch.empty((M, N), dtype=torch.bfloat16, device=dev)
+            d16[:, :N].copy_(dpre)
+            if b is not None:
+                K.colsum(d16, M, N, Np, gb, accumulate=direct)
+            sk = _split_k(N, Kin, M)
+            if sk > 1 and not direct:
+                gW.zero_()
+            K.gemm_bf16(N, Kin, M, d16, Np, 1, xs, Kin, 1, gW, Kin, split_k=sk, accumulate=direct and sk == 1)
+            K.gemm_bf16(M, Kin, Np, d16, Np, 0, ws, Kin, 1, dx, Kin)
+        else:
+            dpre = dpre.contiguous()
+            if b is not None:
+                K.colsum(dpre, M, N, N, gb, accumulate=direct)
+            K.gemm_f32(N, Kin, M, dpre, 1, N, xs, Kin, 1, gW, Kin, accumulate=direct)
+            K.gemm_f32(M, Kin, N, dpre, N, 1, W, Kin, 1, dx, Kin)
+        if direct:
+            runtime.notify_grads((W, b) if b is not None else (W,))
+            gW = gb = None
+        return dx.reshape(shape), gW, gb, None, None, None
+
+
+class AddLayerNormFn(Function):
+    """LayerNorm(a + b) over the last dimension (full_vqa.py:107-108: proj_norm(attflat_x + attflat_y); full_vgd.py:108-109
+    with a broadcast over the regions): the residual + LayerNorm kernel with `a` as the residual input."""
+
+    @staticmethod
+    def forward(ctx, a, b, a2, b2, eps):
+        require_cuda(a, b)
+        shape = b.shape
+        H = shape[-1]
+        z = b.reshape(-1, H).to(torch.float32).clone(memory_format=torch.contiguous_format)
+        res = a.expand(shape).reshape(-1, H).to(torch.float32).contiguous()
+        rows = z.shape[0]
+        out = torch.empty_like(z)
+        mean = torch.empty(rows, dtype=torch.float32, device=z.device)
+        sigma = torch.empty(rows, dtype=torch.float32, device=z.device)
+        K.ln_residual_fwd(rows, H, res, z, a2, b2, eps, out, None, mean, sigma)
+        ctx.save_for_backward(z, mean, sigma, a2)
+        ctx.eps, ctx.shape, ctx.a_shape, ctx.params = eps, shape, a.shape, (a2, b2)
+        return out.view(shape)
+
+    @staticmethod
+    def backward(ctx, dout):
+        z, mean, sigma, a2 = ctx.saved_tensors
+        rows, H = z.shape
+        dout = dout.reshape(rows, H).contiguous()
+        dz = torch.empty_like(z)
+        sinks = _direct(ctx.params)
+        direct = sinks is not None
+        da2, db2 = sinks if direct else (torch.zeros_like(a2), torch.zeros_like(a2))
+        K.ln_residual_bwd(rows, H, dout, z, mean, sigma, a2, ctx.eps, dz, None, da2, db2)
+        dz = dz.view(ctx.shape)
+        da = dz
+        if tuple(ctx.a_shape) != tuple(ctx.shape):          # `a` was broadcast over leading dimensions: sum them back
+            da = dz.sum_to_size(ctx.a_shape)
+        if direct:
+            runtime.notify_grads(ctx.params)
+            return da, dz, None, None, None
+        return da, dz, da2, db2, None
+
+
+# ----------------------------------------------------------------------------------------------------------
 # stand-alone LayerNorm (modules.py:44-56) — same kernel with no residual / dropout
 # ----------------------------------------------------------------------------------------------------------
 class LayerNormFn(Function):

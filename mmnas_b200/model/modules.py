@@ -18,7 +18,8 @@ import torch.nn.functional as F
 from .. import kernels as K
 from .. import runtime
 from .._lib import require_cuda
-from ..functional import AttBlockFn, AttBlockPyFn, FFNBlockFn, FFNBlockPyFn, LayerNormFn, BlockCfg
+from ..functional import (AttBlockFn, AttBlockPyFn, FFNBlockFn, FFNBlockPyFn, LayerNormFn, BlockCfg, LinearFn,
+                          AddLayerNormFn)
 
 
 class RelGeometry:
@@ -115,22 +116,38 @@ class LayerNorm(nn.Module):
         return LayerNormFn.apply(x, self.a_2, self.b_2, self.eps)
 
 
+def linear(x, lin, relu=False, drop=K.NO_DROP):
+    """nn.Linear `lin` (+ReLU, + dropout) on the library GEMMs for CUDA tensors (LinearFn); plain torch for CPU tensors —
+    these layers belong to the callers (stem / heads), not to the operator hot path, so a CPU caller
+    (constructing or inspecting a net) is not an error."""
+    if x.is_cuda:
+        return LinearFn.apply(x, lin.weight, lin.bias, relu, drop, runtime.get_precision())
+    y = lin(x)
+    return F.relu(y) if relu else y
+
+
 class FC(nn.Module):
-    """Parameter container for Linear(+ReLU+dropout).  Inside FeedForward the arithmetic is fused into the block
-    kernels; the stand-alone forward below serves only the task heads (AttFlat), which are outside the
-    operator hot path."""
+    """Linear(+ReLU+dropout), modules.py:13-31.  Inside FeedForward the arithmetic is fused into the block kernels (this
+    module is then a parameter container); the stand-alone forward serves the task heads (AttFlat) and runs on the
+    library GEMM with the bias / ReLU / dropout epilogue."""
 
     def __init__(self, in_size, out_size, dropout_r=0., use_relu=True):
         super().__init__()
         self.dropout_r = dropout_r
         self.use_relu = use_relu
         self.linear = nn.Linear(in_size, out_size)
+        self._site = runtime.new_site()
+        self._ncalls = [0]
 
     def forward(self, x):
-        x = self.linear(x)
-        if self.use_relu:
-            x = F.relu(x)
-        return F.dropout(x, self.dropout_r, self.training) if self.dropout_r > 0 else x
+        drop = K.NO_DROP
+        if self.training and self.dropout_r > 0 and self.use_relu and x.is_cuda:
+            self._ncalls[0] += 1
+            drop = K.Drop(runtime.rng_state(x.device), (self._site << 32) | (self._ncalls[0] & 0xFFFFFFFF), self.dropout_r)
+        x = linear(x, self.linear, self.use_relu, drop)
+        if self.dropout_r > 0 and not drop.active:
+            x = F.dropout(x, self.dropout_r, self.training)
+        return x
 
 
 class MLP(nn.Module):
@@ -140,11 +157,12 @@ class MLP(nn.Module):
         self.linear = nn.Linear(mid_size, out_size)
 
     def forward(self, x):
-        return self.linear(self.fc(x))
+        return linear(self.fc(x), self.linear)
 
 
 class AttFlat(nn.Module):
-    """Attention pooling head (modules.py:59-85).  Caller-side component, kept in PyTorch for now."""
+    """Attention pooling head (modules.py:59-85): MLP -> masked softmax over the sequence -> weighted sum -> merge.
+    The three dense layers run on the library GEMMs; the softmax over <= 100 positions and the pooling stay torch."""
 
     def __init__(self, __C):
         super().__init__()
@@ -158,7 +176,7 @@ class AttFlat(nn.Module):
             att = att.masked_fill(x_mask.squeeze(1).squeeze(1).unsqueeze(2), -1e9)
         att = F.softmax(att, dim=1)
         pooled = torch.einsum('bng,bnh->bgh', att, x).reshape(x.size(0), -1)
-        return self.linear_merge(pooled)
+        return linear(pooled, self.linear_merge)
 
 
 class MHAtt(_OpBase):

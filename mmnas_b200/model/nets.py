@@ -18,7 +18,8 @@ import torch.nn.functional as F
 from .. import runtime
 from ..functional import StemImageFn
 from .mixed import MixedOp
-from .modules import AttFlat, LayerNorm, RelGeometry
+from .modules import AttFlat, LayerNorm, RelGeometry, linear
+from ..functional import AddLayerNormFn
 from ..utils.ops_adapter import OpsAdapter
 
 OPS_ADAPTER = OpsAdapter()
@@ -155,16 +156,21 @@ class _NetBase(nn.Module):
         x_out, y_out = self.backnone(x_in, y_in, x_mask, y_mask, x_rel, y_rel)
         return self.head(x_out, y_out, x_mask, y_mask)
 
+    def _add_norm(self, a, b):
+        """proj_norm(a + b): one residual + LayerNorm kernel on CUDA."""
+        if b.is_cuda:
+            return AddLayerNormFn.apply(a, b, self.proj_norm.a_2, self.proj_norm.b_2, self.proj_norm.eps)
+        return self.proj_norm(a + b)
+
     def head(self, x_out, y_out, x_mask, y_mask):
         if self.task == 'vgd':      # full_vgd.py:105-112
-            xy = self.attflat_x(x_out, x_mask).unsqueeze(1) + self.attfc_y(y_out)
-            xy = self.proj_norm(xy)
-            scores = self.proj_scores(xy).squeeze(-1)
+            xy = self._add_norm(self.attflat_x(x_out, x_mask).unsqueeze(1), linear(y_out, self.attfc_y))
+            scores = linear(xy, self.proj_scores).squeeze(-1)
             if self.SCORES_LOSS == 'kld':
                 scores = F.log_softmax(scores, dim=-1)
-            return scores, self.proj_reg(xy)
-        xy = self.proj_norm(self.attflat_x(x_out, x_mask) + self.attflat_y(y_out, y_mask))
-        out = self.proj(xy)
+            return scores, linear(xy, self.proj_reg)
+        xy = self._add_norm(self.attflat_x(x_out, x_mask), self.attflat_y(y_out, y_mask))
+        out = linear(xy, self.proj)
         if self.task == 'itm':      # full_itm.py:109-110
             out = torch.sigmoid(out.squeeze(-1))
         return out

@@ -328,9 +328,12 @@ def test_direct_gradient_accumulation_equals_autograd_accumulation(mode):
             runtime.direct_grads, runtime.grad_listener = False, None
     assert len(seen) > 2 * 150                               # every block parameter was reported to the reducer, twice
     pr = Parity('direct_grads/%s' % mode)
+    gmax = max(float(p.grad.abs().max()) for p in net_a.parameters())
     for (n_, pa), pb in zip(net_a.named_parameters(), net_b.parameters()):
-        assert pb.grad.data_ptr() == fg.view(fg.params.index(pb)).data_ptr() if False else True
-        pr.add(n_, pb.grad, pa.grad, 2e-5 if mode == 'fp32' else 2e-3, 1e-3 * float(pa.grad.abs().max()), metric='fro')
+        # floor: the bias of AttFlat's logit layer has a zero gradient by construction (softmax is shift invariant), what
+        # is left there is accumulation-order noise
+        pr.add(n_, pb.grad, pa.grad, 2e-5 if mode == 'fp32' else 2e-3, max(1e-3 * float(pa.grad.abs().max()), 1e-4 * gmax),
+               metric='fro')
     pr.check()
 
 
