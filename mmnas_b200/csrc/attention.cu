@@ -6,6 +6,7 @@
 // 4 query rows, lane l owns keys l, l+32, l+64, l+96), nothing but O reaches HBM.  The backward
 // recomputes P from Q, K (+bias, mask, dropout key) instead of reading a saved [B,h,Nq,Nk] map.
 // fp32 math throughout; T (float / bf16) is only the storage type of q, k, v, o and their grads.
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/mmnas_b200.h"
 
@@ -301,6 +302,13 @@ int mmnas_attn_bwd_tc(int B, int heads, int Nq, int Nk, const void* q, long ldq,
                       long lddo, void* dq, long lddq, void* dk, long lddk, void* dv, long lddv, float* dbias, float scale,
                       const unsigned long long* rng_state, unsigned long long salt, float p, cudaStream_t s);
 
+// tuning only (MMNAS_ATTN_TC_MIN_NK): key counts below this take the FFMA kernel in the bf16 arm too
+static int tc_min_nk() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MMNAS_ATTN_TC_MIN_NK"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
 extern "C" int mmnas_attn_fwd(int dtype, int B, int heads, int Nq, int Nk, int head_dim, const void* q, long ldq,
                               const void* k, long ldk, const void* v, long ldv, const unsigned char* kmask,
                               const float* bias, void* o, long ldo, float scale, const unsigned long long* rng_state,
@@ -309,7 +317,7 @@ extern "C" int mmnas_attn_fwd(int dtype, int B, int heads, int Nq, int Nk, int h
   if (rc) return rc;
   if (B == 0) return MMNAS_OK;
   MMNAS_CHECK_ARG(q && k && v && o, "attn_fwd: null operand");
-  if (dtype == 1) {   // bf16 arm: tcgen05 kernel; the FFMA kernel below only if TMA cannot address the operands
+  if (dtype == 1 && Nk >= tc_min_nk()) {   // bf16 arm: tcgen05 kernel; the FFMA kernel below only if TMA cannot address the operands
     rc = mmnas_attn_fwd_tc(B, heads, Nq, Nk, q, ldq, k, ldk, v, ldv, kmask, bias, o, ldo, scale, rng_state, salt, p,
                            (cudaStream_t)stream);
     if (rc != MMNAS_ERR_UNSUPPORTED) return rc;
@@ -345,7 +353,7 @@ extern "C" int mmnas_attn_bwd(int dtype, int B, int heads, int Nq, int Nk, int h
   if (rc) return rc;
   if (B == 0) return MMNAS_OK;
   MMNAS_CHECK_ARG(q && k && v && o && dout && dq && dk && dv, "attn_bwd: null operand");
-  if (dtype == 1) {
+  if (dtype == 1 && Nk >= tc_min_nk()) {
     rc = mmnas_attn_bwd_tc(B, heads, Nq, Nk, q, ldq, k, ldk, v, ldv, kmask, bias, o, ldo, dout, lddo, dq, lddq, dk, lddk,
                            dv, lddv, dbias, scale, rng_state, salt, p, (cudaStream_t)stream);
     if (rc != MMNAS_ERR_UNSUPPORTED) return rc;

@@ -112,17 +112,28 @@ __device__ __forceinline__ void chunk_logits(const AttnTcArgs& a, const RowCtx& 
   }
 }
 
-// dropout multipliers of 4 consecutive keys j..j+3 (j % 4 == 0) of this row: one hash when the row is 4-aligned
-template <bool VEC>
-__device__ __forceinline__ void drop4(const AttnTcArgs& a, const RowCtx& c, uint64_t key, int j, float (&m)[4]) {
-  if (VEC) {
-    const uint64_t r = mmnas_mix64(key ^ (((c.rowbase + j) >> 2) * 0x9E3779B97F4A7C15ull));
+// Dropout decisions of the 32 keys [j0, j0 + 32) of this thread's row as one bit per key (1 = kept).  The stream is the
+// library's: element e = rowbase + j of the flattened [B, heads, Nq, Nk] map takes 16 bits of hash(key, e >> 2).  A row
+// that does not start on a multiple of 4 (Nk % 4 != 0: the 14 / 15 / 50-key shapes) shares its first and last hash with
+// its neighbours, so a chunk needs 9 hashes instead of 8 — not one per element, which is what made the unaligned
+// shapes 3-4x more expensive than the aligned ones.
+__device__ __forceinline__ uint32_t chunk_keep_bits(const AttnTcArgs& a, const RowCtx& c, uint64_t key, int j0) {
+  const uint64_t e0 = c.rowbase + (uint64_t)j0;
+  const uint64_t g0 = e0 >> 2;
+  const int o = (int)(e0 & 3);                 // position of column j0 inside its hash group
+  uint32_t bits = 0;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) m[u] = ((unsigned)(r >> (16 * u)) & 0xFFFFu) < a.drop.thresh ? 0.f : a.drop.scale;
-  } else {
+  for (int g = 0; g < 9; ++g) {
+    if (g == 8 && o == 0) break;
+    const uint64_t r = mmnas_mix64(key ^ ((g0 + g) * 0x9E3779B97F4A7C15ull));
 #pragma unroll
-    for (int u = 0; u < 4; ++u) m[u] = drop_mult(key, c.rowbase + j + u, a.drop.thresh, a.drop.scale);
+    for (int u = 0; u < 4; ++u) {
+      const int t = 4 * g + u - o;             // column offset inside the chunk
+      const uint32_t kept = (((unsigned)(r >> (16 * u)) & 0xFFFFu) < a.drop.thresh) ? 0u : 1u;
+      if (t >= 0 && t < 32) bits |= kept << t;
+    }
   }
+  return bits;
 }
 
 __device__ __forceinline__ void tc_prologue(uint32_t bar_base, int nbars, uint32_t* tmem_slot, uint32_t cols, int warp) {
@@ -211,14 +222,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       sum += s[t];
     }
     if (use_drop && row_ok) {
+      const uint32_t kbits = chunk_keep_bits(a, ctx, key, cc * 32);
 #pragma unroll
-      for (int g = 0; g < 8; ++g)
-        if (cc * 32 + 4 * g < Nk) {
-          float m[4];
-          drop4<VEC>(a, ctx, key, cc * 32 + 4 * g, m);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) s[4 * g + u] *= m[u];
-        }
+      for (int t = 0; t < 32; ++t) s[t] = ((kbits >> t) & 1u) ? s[t] * a.drop.scale : 0.f;
     }
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -316,6 +322,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   // sum_j dS_ij cancels to fp32 rounding.  (Taking it from the bf16-rounded O and dO in global memory left a
   // residue of ~2^-9 |delta| in every row sum, which is what d linear_r.bias = sum dS / r accumulates.)
   float mx = -INFINITY, sum = 0.f, num = 0.f;
+  uint32_t kb0 = 0xFFFFFFFFu, kb1 = 0xFFFFFFFFu, kb2 = 0xFFFFFFFFu, kb3 = 0xFFFFFFFFu;    // dropout keep bits, hashed once
 #pragma unroll 1
   for (int cc = 0; cc < NC; ++cc) {
     uint32_t r[32], rp[32];
@@ -331,10 +338,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     const float nm = fmaxf(mx, cm);                 // finite from chunk 0 on: key 0 is never -inf
     const float nml = nm * LOG2E;
     float part = 0.f, pnum = 0.f;
+    const uint32_t kbits = use_drop ? chunk_keep_bits(a, ctx, key, cc * 32) : 0xFFFFFFFFu;
+    const float dscale1 = use_drop ? a.drop.scale : 1.f;
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
-      float m[4] = {1.f, 1.f, 1.f, 1.f};
-      if (use_drop && cc * 32 + 4 * g < Nk) drop4<VEC>(a, ctx, key, cc * 32 + 4 * g, m);
+      float m[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) m[u] = ((kbits >> (4 * g + u)) & 1u) ? dscale1 : 0.f;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int t = 4 * g + u;
@@ -351,6 +361,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     sum = fmaf(sum, f, part);
     num = fmaf(num, f, pnum);
     mx = nm;
+    if (cc < 2) { if (cc == 0) kb0 = kbits; else kb1 = kbits; } else { if (cc == 2) kb2 = kbits; else kb3 = kbits; }
   }
   const float mxl = mx * LOG2E;
   const float inv = (row_ok && sum > 0.f) ? 1.f / sum : 0.f;     // rows >= Nq contribute zeros to dK / dV
@@ -366,10 +377,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     tmem_ld_wait();
     chunk_logits(a, ctx, cc, r, bb, s);
     const uint32_t mk = chunk_mask(ctx, cc);
+    const uint32_t kbits = cc < 2 ? (cc == 0 ? kb0 : kb1) : (cc == 2 ? kb2 : kb3);      // the masks pass 1 hashed
+    const float dscale = use_drop ? a.drop.scale : 1.f;
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
-      float m[4] = {1.f, 1.f, 1.f, 1.f};
-      if (use_drop && cc * 32 + 4 * g < Nk) drop4<VEC>(a, ctx, key, cc * 32 + 4 * g, m);
+      float m[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) m[u] = ((kbits >> (4 * g + u)) & 1u) ? dscale : 0.f;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int t = 4 * g + u;

@@ -56,7 +56,7 @@ class FlatGrads:
 class BucketReducer:
     """Overlapped gradient mean over the process group, on top of FlatGrads."""
 
-    def __init__(self, flat_grads, group=None, bucket_mb=25.0):
+    def __init__(self, flat_grads, group=None, bucket_mb=60.0):
         self.fg = flat_grads
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -390,7 +390,7 @@ def tree_leaves(obj):
 class TrainStep:
     """net_optim.zero_grad(); pred = net(x); loss = BCE_sum; backward (+ overlapped grad mean); clip; Adam."""
 
-    def __init__(self, net, lr_base=0.00012, epoch_steps=1000, bucket_mb=25.0, use_graph=False, loss_fn=vqa_loss,
+    def __init__(self, net, lr_base=0.00012, epoch_steps=1000, bucket_mb=60.0, use_graph=False, loss_fn=vqa_loss,
                  betas=(0.9, 0.98), eps=1e-9, clip=1.0):
         self.net = net
         self.loss_fn = loss_fn
@@ -481,7 +481,7 @@ class SearchStep:
     architecture step in MODE 'full' on a held-out batch."""
 
     def __init__(self, net, lr_base=0.0004, epoch_steps=1000, alpha_lr=0.1, alpha_betas=(0., 0.999), mode='full',
-                 bucket_mb=25.0, loss_fn=vqa_loss, use_executor=True):
+                 bucket_mb=60.0, loss_fn=vqa_loss, use_executor=True):
         self.net = net
         self.mode = mode
         self.loss_fn = loss_fn
