@@ -129,6 +129,59 @@ def cpu_baseline(seconds=12.0, batch=BATCH):
             'sample': '%d train steps of %s, torch CPU fp32, batch %d, %.2f s/step, after 1 warm-up' % (n, what, batch, dt)}
 
 
+def gpu_eager_reference(dev, steps=5, batch=BATCH):
+    """The bar BASELINE.md names: the UNMODIFIED reference (baseline/_ref: full_vqa.Net_Full, its PyTorch operators, its
+    WarmupOptimizer) running eagerly on the SAME GPU, float32 (TF32 off, as the reference leaves it), step body of
+    train_vqa.py:294-311, B=64, dropout 0.1, device-resident batch, CUDA events.  None when baseline/_ref is absent."""
+    if not reference_available():
+        return None
+    import torch
+    from mmnas_b200 import genotypes
+    from mmnas_b200.data.synthetic import Cfg, SynthSpec, make_batch, init_dict
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = True           # torch defaults: what the reference runs with
+    try:
+        sys.path.insert(1, REF_DIR)
+        from mmnas.model.full_vqa import Net_Full
+        from mmnas.utils.optimizer import WarmupOptimizer
+        torch.manual_seed(888)
+        spec = SynthSpec(batch=batch)
+        cfg = Cfg(genotype=genotypes.shipped('mmnas_vqa'))
+        inputs, target = make_batch(spec)
+        net = Net_Full(cfg, init_dict(spec)).to(dev).train()
+        optim = WarmupOptimizer(cfg.NET_LR_BASE, torch.optim.Adam(net.parameters(), lr=0, betas=cfg.OPT_BETAS, eps=cfg.OPT_EPS),
+                                10 ** 6, warmup=True)
+        loss_fn = torch.nn.BCEWithLogitsLoss(reduction='sum')
+        inputs, target = tuple(t.to(dev) for t in inputs), target.to(dev)
+
+        def step():
+            optim.zero_grad()
+            loss = loss_fn(net(inputs), target)
+            loss += 0 * sum(p.sum() for p in net.parameters())
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(net.parameters(), cfg.NET_GRAD_CLIP)
+            optim.step()
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        del net, optim
+        torch.cuda.empty_cache()
+        return {'value': batch / ms * 1e3, 'unit': 'samples/s', 'ms_per_step': ms,
+                'how': 'the unmodified reference (baseline/_ref) eager on this GPU: full_vqa.Net_Full + its PyTorch operators + '
+                       'WarmupOptimizer, fp32 (matmul TF32 off), batch %d, dropout 0.1, device-resident batch, %d steps after 3 '
+                       'warm-up, CUDA events' % (batch, steps)}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -471,8 +524,9 @@ def run_b200(args):
         torch.cuda.empty_cache()
         workloads = run_workloads(args, world, rank, dev, barrier)
 
-    cpu = None
+    cpu = gpu_ref = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        gpu_ref = gpu_eager_reference(dev)
         cpu = cpu_baseline()
 
     if rank == 0:
@@ -496,6 +550,8 @@ def run_b200(args):
             line['workloads'] = workloads
         if cpu:
             line['cpu_baseline'] = cpu
+        if gpu_ref:
+            line['reference_gpu_eager'] = gpu_ref
         emit(line)
     if world > 1:
         # a captured graph that contains NCCL kernels keeps the communicator busy at teardown; all results are
