@@ -476,12 +476,18 @@ class TrainStep:
         return self._static_in, self._static_tgt
 
 
+class _Segments:
+    """State of SearchStep's segmented replay: static inputs, the tensors handed from one segment to the next, the four
+    captured graphs."""
+    key = ex_key = inputs = target = x_in = y_in = x_mask = y_mask = x_out = y_out = loss = graphs = None
+
+
 class SearchStep:
     """One iteration of search_vqa.py:278-337: weight step on the sampled path, and (when `arch=True`) the
     architecture step in MODE 'full' on a held-out batch."""
 
     def __init__(self, net, lr_base=0.0004, epoch_steps=1000, alpha_lr=0.1, alpha_betas=(0., 0.999), mode='full',
-                 bucket_mb=60.0, loss_fn=vqa_loss, use_executor=True):
+                 bucket_mb=60.0, loss_fn=vqa_loss, use_executor=True, segments=True):
         self.net = net
         self.mode = mode
         self.loss_fn = loss_fn
@@ -499,8 +505,15 @@ class SearchStep:
             from .executor import SearchExecutor
             self.executor = SearchExecutor(net)
         object.__setattr__(net, '_executor', self.executor)
+        # Segmented replay (see _Segments): everything around the sampled backbone is static, so it replays from four
+        # CUDA graphs while the backbone stays a sequence of block-level calls chosen per step.
+        self.use_segments = (segments and self.executor is not None
+                             and os.environ.get('MMNAS_SEARCH_SEGMENTS', '1') != '0')
+        self._seg = None
 
     def _forward_backward(self, inputs, target):
+        if self.use_segments:
+            return self._segmented(inputs, target)
         self.grads.zero()                # net.zero_grad() + the reference's 0*sum(params) dummy terms
         self.reducer.reset()
         runtime.advance(self.grads.flat.device)
@@ -516,6 +529,124 @@ class SearchStep:
             runtime.direct_grads, runtime.grad_listener = False, None
         self.reducer.finish()
         return loss.detach()
+
+    # ---- segmented replay ------------------------------------------------------------------------------------------
+    # A: zero gradients, advance the dropout counter, refresh the bf16 weight shadows, stem forward (embedding, LSTM,
+    #    region projection, masks, box geometry), stage the executor's inputs
+    #    -> executor.run_forward(): eager block-level calls along the sampled path (or all candidates, MODE 'full')
+    # B: heads + loss forward and backward, output gradients staged for the executor
+    #    -> executor.run_backward()
+    # C: stem backward (region projection, LSTM, embedding)
+    #    -> gradient mean over ranks (eager NCCL, world > 1)
+    # D: clip + Adam (weight step only)
+    # A and C share one autograd graph, exactly as torch.cuda.make_graphed_callables splits forward and backward.
+    def _seg_a(self, seg):
+        self.grads.zero()
+        runtime.advance(self.grads.flat.device)
+        if runtime.get_precision() == 'bf16':
+            self.shadows.refresh()
+        x_in, y_in, x_mask, y_mask, _, g4 = self.net.stem(seg.inputs)
+        ex = self.executor
+        ex.prepare(x_in, y_in)
+        ex.stage(x_in, y_in, x_mask, y_mask, g4)
+        seg.x_in, seg.y_in, seg.x_mask, seg.y_mask = x_in, y_in, x_mask, y_mask
+
+    def _seg_b(self, seg):
+        ex = self.executor
+        if seg.x_out is None or seg.x_out.data_ptr() != ex.xs[-1].data_ptr():
+            seg.x_out = ex.xs[-1].detach().requires_grad_(True)      # leaves aliasing the executor's output buffers
+            seg.y_out = ex.ys[-1].detach().requires_grad_(True)
+        seg.x_out.grad = seg.y_out.grad = None
+        loss = self.loss_fn(self.net.head(seg.x_out, seg.y_out, seg.x_mask, seg.y_mask), seg.target)
+        loss.backward()
+        for dst, leaf in ((ex.dxs[-1], seg.x_out), (ex.dys[-1], seg.y_out)):
+            if leaf.grad is None:
+                dst.zero_()
+            else:
+                dst.copy_(leaf.grad)
+        seg.x_out.grad = seg.y_out.grad = None
+        seg.loss = loss.detach()
+
+    def _seg_c(self, seg):
+        ex = self.executor
+        torch.autograd.backward([seg.x_in, seg.y_in], [ex.dxs[0], ex.dys[0]])
+        seg.x_in = seg.y_in = None
+
+    def _seg_d(self, seg):
+        self.optim.clip_and_step()
+
+    def _reduce(self):
+        if self.reducer.enabled:
+            self.reducer.reset()
+            self.reducer.finish()
+
+    def _seg_key(self, inputs, target):
+        return (tuple((tuple(t.shape), t.dtype) for t in tree_leaves(inputs) + tree_leaves(target)),
+                runtime.get_precision(), self.net.training)
+
+    def _capture_segments(self, inputs, target):
+        """Warm up eagerly (plans, allocator pools, cuDNN handles), then capture A-D into one memory pool.  Whatever
+        the warm-up mutates is restored, so the first replayed step is the first update."""
+        seg = _Segments()
+        seg.key = self._seg_key(inputs, target)
+        seg.inputs = tree_map(torch.clone, inputs)
+        seg.target = tree_map(torch.clone, target)
+        ex = self.executor
+        f = self.optim.fused
+        state = list(self.net_params) + [f.exp_avg, f.exp_avg_sq, f.state, runtime.rng_state(self.grads.flat.device)]
+        saved = [t.detach().clone() for t in state]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._seg_a(seg)
+                ex.run_forward()
+                self._seg_b(seg)
+                ex.run_backward()
+                self._seg_c(seg)
+                self._seg_d(seg)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        pool = torch.cuda.graph_pool_handle()
+        seg.graphs = []
+        for body in (self._seg_a, self._seg_b, self._seg_c, self._seg_d):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                body(seg)
+            seg.graphs.append(g)
+        seg.ex_key = ex.key
+        with torch.no_grad():
+            for t, v in zip(state, saved):
+                t.copy_(v)
+        torch.cuda.synchronize()
+        self._seg = seg
+
+    def _segmented(self, inputs, target):
+        seg = self._seg
+        self.reducer._armed = False          # no per-parameter hooks: the mean over ranks runs once, after segment C
+        runtime.direct_grads, runtime.grad_listener = True, None
+        runtime.shadows_fresh = runtime.get_precision() == 'bf16'
+        try:
+            if seg is None or seg.key != self._seg_key(inputs, target) or seg.ex_key != self.executor.key:
+                self._seg = None
+                self._capture_segments(inputs, target)
+                seg = self._seg
+            for dst, src in zip(tree_leaves(seg.inputs) + tree_leaves(seg.target),
+                                tree_leaves(inputs) + tree_leaves(target)):
+                if dst.data_ptr() != src.data_ptr():
+                    dst.copy_(src, non_blocking=True)
+            ga, gb, gc, gd = seg.graphs
+            ex = self.executor
+            ga.replay()
+            ex.run_forward()
+            gb.replay()
+            ex.run_backward()
+            gc.replay()
+            self._reduce()
+        finally:
+            runtime.shadows_fresh = False
+            runtime.direct_grads, runtime.grad_listener = False, None
+        return seg.loss.clone()
 
     def _off(self):
         # Net_Search.unused_modules_off/back (hygr_vqa.py:175-196) swap the candidates that do not run for None; the
@@ -535,7 +666,10 @@ class SearchStep:
         try:
             self.optim.set_lr()
             loss = self._forward_backward(inputs, target)
-            self.optim.clip_and_step()
+            if self.use_segments:
+                self._seg.graphs[3].replay()
+            else:
+                self.optim.clip_and_step()
         finally:
             self._back()
         return loss

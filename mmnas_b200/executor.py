@@ -207,7 +207,8 @@ class SearchExecutor:
             buf = self.cand_out[key] = torch.empty_like(ref)
         return buf
 
-    def forward(self, x_in, y_in, x_mask, y_mask, g4):
+    def prepare(self, x_in, y_in):
+        """(Re)build the static plans when the problem shape, device, precision arm or train/eval mode changed."""
         B, Nx, H = x_in.shape
         Ny = y_in.shape[1]
         dev = x_in.device
@@ -216,16 +217,24 @@ class SearchExecutor:
         if self.key != key:
             self._build(B, Nx, Ny, H, dev, bf)
             self.key = key
-        full = MixedOp.MODE == 'full'
-        self.full = full
+
+    def stage(self, x_in, y_in, x_mask, y_mask, g4):
+        """Copy the stem's outputs into the static input buffers (device-side work only: capturable)."""
         self.xs[0].copy_(x_in)
         self.ys[0].copy_(y_in)
-        self.xmask.copy_(x_mask.reshape(B, Nx))
-        self.ymask.copy_(y_mask.reshape(B, Ny))
+        self.xmask.copy_(x_mask.reshape(self.xmask.shape))
+        self.ymask.copy_(y_mask.reshape(self.ymask.shape))
         self.g4.copy_(g4)
-        if bf:
+        if self.bf:
             K.cast_bf16(self.xs[0], self.x16s[0])
             K.cast_bf16(self.ys[0], self.y16s[0])
+
+    def run_forward(self):
+        """The 30 nodes over the staged inputs: the sampled candidate per node (MODE None) or every candidate and
+        the gate-weighted sum (MODE 'full').  Results in xs[-1] / ys[-1]."""
+        bf = self.bf
+        full = MixedOp.MODE == 'full'
+        self.full = full
         stream = _lib.stream()
         self.picks_x = [m.active_index[0] for m in self.nodes_x]
         self.picks_y = [m.active_index[0] for m in self.nodes_y]
@@ -246,13 +255,14 @@ class SearchExecutor:
                     K.mixed_accum(outs, gates[i].data, bufs[i + 1])
                     if bf:
                         K.cast_bf16(bufs[i + 1], b16s[i + 1])
+
+    def forward(self, x_in, y_in, x_mask, y_mask, g4):
+        self.prepare(x_in, y_in)
+        self.stage(x_in, y_in, x_mask, y_mask, g4)
+        self.run_forward()
         return self.xs[-1].detach(), self.ys[-1].detach()
 
     def backward(self, dx_out, dy_out):
-        stream = _lib.stream()
-        dev = self.xs[0].device
-        side_stream = runtime.side_stream(dev).cuda_stream if (self.bf and runtime.overlap_wgrad) else None
-        full = self.full
         if dx_out is None:
             self.dxs[-1].zero_()
         else:
@@ -261,6 +271,15 @@ class SearchExecutor:
             self.dys[-1].zero_()
         else:
             self.dys[-1].copy_(dy_out)
+        return self.run_backward()
+
+    def run_backward(self):
+        """Backward of run_forward() from the output gradients staged in dxs[-1] / dys[-1]; input gradients in
+        dxs[0] / dys[0], parameter gradients accumulated straight into the flat gradient buffer."""
+        stream = _lib.stream()
+        dev = self.xs[0].device
+        side_stream = runtime.side_stream(dev).cuda_stream if (self.bf and runtime.overlap_wgrad) else None
+        full = self.full
         listener = runtime.grad_listener
         used_rel = False
         for side, cands, picks, bufs, dbufs, gates, dcand in (

@@ -64,6 +64,7 @@ class _OpBase(nn.Module):
     def _init_runtime(self, n_sites):
         self._sites = [runtime.new_site() for _ in range(n_sites)]
         self._calls = 0
+        self._epoch = -1
         self._w16 = {}
         self.precision = None      # None -> follow mmnas_b200.set_precision()
 
@@ -73,6 +74,8 @@ class _OpBase(nn.Module):
     def _drops(self, x, p):
         if not (self.training and p > 0):
             return tuple(K.NO_DROP for _ in self._sites)
+        if self._epoch != runtime.epoch:        # calls are numbered within a step (runtime.call_index)
+            self._epoch, self._calls = runtime.epoch, 0
         self._calls += 1
         st = runtime.rng_state(x.device)
         return tuple(K.Drop(st, (s << 32) | (self._calls & 0xFFFFFFFF), p) for s in self._sites)
@@ -138,10 +141,13 @@ class FC(nn.Module):
         self.linear = nn.Linear(in_size, out_size)
         self._site = runtime.new_site()
         self._ncalls = [0]
+        self._epoch = [-1]
 
     def forward(self, x):
         drop = K.NO_DROP
         if self.training and self.dropout_r > 0 and self.use_relu and x.is_cuda:
+            if self._epoch[0] != runtime.epoch:
+                self._epoch[0], self._ncalls[0] = runtime.epoch, 0
             self._ncalls[0] += 1
             drop = K.Drop(runtime.rng_state(x.device), (self._site << 32) | (self._ncalls[0] & 0xFFFFFFFF), self.dropout_r)
         x = linear(x, self.linear, self.use_relu, drop)

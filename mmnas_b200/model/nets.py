@@ -122,7 +122,9 @@ class _NetBase(nn.Module):
         if not hasattr(self, 'linear_y_rel'):
             self.linear_y_rel = nn.Linear(4, __C.REL_SIZE)
 
-    def forward(self, input):
+    def stem(self, input):
+        """Everything in front of the backbone (full_vqa.py:90-103): question embedding + LSTM, region projection, the
+        two padding masks, and the pairwise box geometry when the loader ships raw boxes."""
         frcn_feat, bbox_feat, y_rel, ques_ix, x_rel = input
         x_mask = make_mask(ques_ix.unsqueeze(2))
         x_in, _ = self.lstm(self.embedding(ques_ix))
@@ -143,6 +145,10 @@ class _NetBase(nn.Module):
             require_cuda(y_rel)
             pad = y_mask.reshape(y_mask.shape[0], -1).contiguous().view(torch.uint8)
             y_rel = K.box_geometry(y_rel.contiguous().float(), pad)
+        return x_in, y_in, x_mask, y_mask, x_rel, y_rel
+
+    def forward(self, input):
+        x_in, y_in, x_mask, y_mask, x_rel, y_rel = self.stem(input)
         ex = getattr(self, '_executor', None)
         if ex is not None and ex.usable(self.rel_mode):
             # engine search step: the whole supernet backbone is one autograd node over static per-candidate plans

@@ -72,8 +72,16 @@ def manual_seed(seed, device=None):
     st.copy_(torch.tensor([int(seed) & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64))
 
 
+# Host-side twin of the step counter.  Dropout sites number their calls WITHIN a step: a module that runs several times
+# per step (the ITM forwards of the per-module path) gets a fresh mask per call; across steps the device counter supplies
+# the fresh stream.  A captured step (call index baked in at capture) and an eager step therefore draw the same masks.
+epoch = 0
+
+
 def advance(device=None):
     """Bump the step counter: call once per training step (captured fine inside a CUDA graph)."""
+    global epoch
+    epoch += 1
     st = rng_state(device if device is not None else torch.device('cuda', torch.cuda.current_device()))
     kernels.rng_advance(st)
 

@@ -47,3 +47,29 @@ for k, us, n in rows[:40]:
 if len(sys.argv) > 2:
     json.dump({'workload': what, 'gpu_us_per_step': tot, 'library_us': ours, 'other_us': tot - ours,
                'kernels': [{'kernel': k[:160], 'us_per_step': us, 'launches_per_step': n} for k, us, n in rows]}, open(sys.argv[2], 'w'), indent=1)
+
+if os.environ.get('MMNAS_TIMELINE', '0') == '1':
+    # Device timeline: union of kernel intervals (busy), wall span per step, and the largest idle gaps with their neighbours.
+    from torch.autograd import DeviceType
+    ev = sorted(((e.time_range.start, e.time_range.end, e.name) for e in prof.events() if e.device_type == DeviceType.CUDA),
+                key=lambda t: t[0])
+    span = ev[-1][1] - ev[0][0]
+    busy, cur_s, cur_e, gaps = 0.0, ev[0][0], ev[0][1], []
+    last_name = ev[0][2]
+    for s, e, n in ev[1:]:
+        if s > cur_e:
+            busy += cur_e - cur_s
+            gaps.append((s - cur_e, last_name[:60], n[:60]))
+            cur_s, cur_e = s, e
+        else:
+            cur_e = max(cur_e, e)
+        if e >= cur_e: last_name = n
+    busy += cur_e - cur_s
+    gaps.sort(key=lambda g: -g[0])
+    print('timeline: span %.0f us/step, busy (union) %.0f us/step, idle %.0f us/step in %d gaps/step' % (span / N, busy / N, (span - busy) / N, len(gaps) / N))
+    hist = {}
+    for g, a, b_ in gaps:
+        k = (a.split('(')[0][-40:], b_.split('(')[0][-40:])
+        hist.setdefault(k, [0, 0.0]); hist[k][0] += 1; hist[k][1] += g
+    for k, (c, t) in sorted(hist.items(), key=lambda kv: -kv[1][1])[:25]:
+        print('  idle %7.1f us/step over %5.1f gaps/step  after %-40s before %s' % (t / N, c / N, k[0], k[1]))

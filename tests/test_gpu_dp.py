@@ -152,3 +152,66 @@ def test_two_rank_train_steps_keep_replicas_identical(use_graph):
     assert torch.equal(got[0][0], got[1][0])            # parameters after four updates
     assert got[0][2] != got[1][2]                       # the ranks really saw different batches
     assert all(l == l and l < 1e6 for l in got[0][2] + got[1][2])
+
+
+def _search_worker(rank, world, port, q):
+    import mmnas_b200
+    from mmnas_b200.data.synthetic import Cfg, SynthSpec, make_batch, init_dict
+    from mmnas_b200.engine import SearchStep
+    from mmnas_b200.model.nets import Net_Search
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    mmnas_b200.set_precision('bf16')
+    torch.manual_seed(888)
+    spec = SynthSpec(batch=8 * world, vocab=500, n_ans=50)
+    cfg = Cfg(mode='search', DROPOUT_R=0.1)
+    inputs, target = make_batch(spec, seed=11)
+    net = Net_Search(cfg, init_dict(spec)).to(dev).train()
+    sl = slice(8 * rank, 8 * rank + 8)
+    din, dt = tuple(t[sl].to(dev) for t in inputs), target[sl].to(dev)
+    torch.manual_seed(100 + rank)            # different generator state per rank: the picks must still agree
+    step = SearchStep(net, lr_base=1e-3, epoch_steps=1, bucket_mb=8.0)
+    assert step.use_segments and step.reducer.enabled
+    losses, picks = [], []
+    for _ in range(3):
+        losses.append(float(step.weight_step(din, dt)))
+        picks.append([m.active_index[0] for m in net.redundant_modules])
+        losses.append(float(step.arch_step(din, dt)))
+        picks.append([m.active_index[0] for m in net.redundant_modules])
+    torch.cuda.synchronize()
+    flat = torch.cat([p.detach().flatten() for p in net.parameters()]).cpu()
+    q.put((rank, flat.numpy(), picks, losses))
+    q.close()
+    q.join_thread()
+    dist.barrier()
+    torch.cuda.synchronize()
+    os._exit(0)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+@pytest.mark.timeout(300)
+def test_two_rank_search_steps_keep_replicas_identical():
+    """Three weight + architecture iterations of SearchStep (segmented replay, sampled path broadcast from rank 0,
+    gradient mean over ranks after the stem backward): both replicas walk the same paths and hold bit-identical
+    weights and architecture parameters at the end, although they see different data and generator states."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_search_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(world):
+        r, flat, picks, losses = q.get(timeout=240)
+        got[r] = (torch.from_numpy(flat), picks, losses)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0][1] == got[1][1]
+    assert len({tuple(p) for p in got[0][1]}) > 1
+    assert torch.equal(got[0][0], got[1][0])
+    assert got[0][2] != got[1][2]
+    assert all(l == l and l < 1e6 for l in got[0][2] + got[1][2])

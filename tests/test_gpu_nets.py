@@ -610,6 +610,52 @@ def test_search_executor_equals_the_module_path(mode):
     assert torch.allclose(e[6], m[6], atol=1e-3)
 
 
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_search_segmented_replay_equals_eager_steps(mode):
+    """SearchStep replays the stem, the heads + loss, the stem backward and clip + Adam from four CUDA graphs around
+    the eagerly launched backbone.  Same seed, data and dropout state as the fully eager step: identical sampled
+    paths, and the first weight step (capture + first replay) leaves identical parameters, moments and gradients —
+    capture warm-up must not leak into training state.  Later steps follow the eager trajectory up to the usual
+    Adam(eps=1e-9) sensitivity, checked on the losses."""
+    import copy
+    import mmnas_b200
+    from mmnas_b200.engine import SearchStep
+    from mmnas_b200.model.nets import Net_Search
+    torch.manual_seed(888)
+    spec, cfg, init, inputs, target = _search_setup(8, p=0.1)
+    net_a = Net_Search(cfg, init).to(DEV).train()
+    net_b = copy.deepcopy(net_a)
+    din, dt = tuple(t.to(DEV) for t in inputs), target.to(DEV)
+    res = {}
+    with mmnas_b200.precision(mode):
+        for tag, net, seg in (('segments', net_a, True), ('eager', net_b, False)):
+            step = SearchStep(net, lr_base=1e-4, segments=seg)
+            assert step.use_segments == seg
+            mmnas_b200.manual_seed(5)
+            torch.manual_seed(888)
+            l0 = float(step.weight_step(din, dt))
+            first = (torch.cat([q.detach().flatten() for q in net.net_parameters()]).clone(), step.grads.flat.clone(),
+                     step.optim.fused.exp_avg.clone(), int(step.optim.fused.state[1].item()))
+            losses, picks = [l0], [[m.active_index[0] for m in net.redundant_modules]]
+            for it in range(3):
+                losses.append(float(step.arch_step(din, dt)))
+                picks.append([m.active_index[0] for m in net.redundant_modules])
+                losses.append(float(step.weight_step(din, dt)))
+                picks.append([m.active_index[0] for m in net.redundant_modules])
+            alphas = torch.cat([q.detach().reshape(-1) for q in net.alpha_prob_parameters()])
+            res[tag] = (first, losses, picks, alphas)
+    s, e = res['segments'], res['eager']
+    assert s[2] == e[2]
+    assert s[0][3] == e[0][3] == 1                                   # one Adam step counted, not 1 + warm-ups
+    assert normwise(s[0][1], e[0][1]) < 1e-5                         # first-step gradients
+    assert normwise(s[0][2], e[0][2]) < 1e-5                         # first moments
+    assert (s[0][0] - e[0][0]).abs().max().item() <= 0.05 * 1e-4     # parameters: a small fraction of one lr-sized step
+    assert abs(s[1][0] - e[1][0]) <= 1e-6 * abs(e[1][0])
+    for a, b in zip(s[1], e[1]):
+        assert abs(a - b) <= (2e-3 if mode == 'fp32' else 2e-2) * abs(b)
+    assert torch.allclose(s[3], e[3], atol=2e-2)
+
+
 def test_batched_sampling_on_cuda_draws_what_per_module_binarize_draws():
     """The CUDA generator twin of tests/test_host_logic.py: one exponential_ per node + batched argmax reproduces
     torch.multinomial's picks (the reference's MixedOp.binarize) under the same seed."""
