@@ -507,6 +507,7 @@ class SearchStep:
         object.__setattr__(net, '_executor', self.executor)
         # Segmented replay (see _Segments): everything around the sampled backbone is static, so it replays from four
         # CUDA graphs while the backbone stays a sequence of block-level calls chosen per step.
+        self.presample = self.net_params[0].is_cuda and os.environ.get('MMNAS_PRESAMPLE', '1') != '0'
         self.use_segments = (segments and self.executor is not None
                              and os.environ.get('MMNAS_SEARCH_SEGMENTS', '1') != '0')
         self._seg = None
@@ -672,6 +673,7 @@ class SearchStep:
                 self.optim.clip_and_step()
         finally:
             self._back()
+        self._presample()
         return loss
 
     def arch_step(self, inputs, target):
@@ -684,10 +686,17 @@ class SearchStep:
             self.alpha_optim.step()
             if MixedOp.MODE == 'two':
                 self.net.rescale_updated_arch_param()
+            self.net.alphas_updated()
         finally:
             self._back()
             MixedOp.MODE = None
+        self._presample()
         return loss
+
+    def _presample(self):
+        # next step's draw, issued now on the sampling stream (nets.py: presample); MODE 'two' samples per module
+        if self.presample and self.mode != 'two':
+            self.net.presample()
 
     def __call__(self, train_batch, eval_batch=None):
         loss = self.weight_step(*train_batch)

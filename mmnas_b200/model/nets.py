@@ -295,9 +295,21 @@ class Net_Search(_NetBase):
         Under data parallelism the picks are broadcast from rank 0, so every rank runs the same path by construction
         (the reference relies on identically seeded ranks).  Not for MODE 'two'."""
         if not batched:
+            self.__dict__.pop('_presampled', None)
             for m in self.redundant_modules:
                 m.binarize()
             return
+        pre = self.__dict__.pop('_presampled', None)
+        if pre is not None and self._presample_valid(pre, group):
+            pre['done'].synchronize()                                  # normally long complete: drawn a step ago
+            torch.cuda.current_stream(pre['picks'].device).wait_event(pre['done'])
+            pre['picks'].record_stream(torch.cuda.current_stream(pre['picks'].device))
+            self._apply_picks(pre['picks'], pre['host'].tolist())
+            return
+        picks = self._draw_picks(group)
+        self._apply_picks(picks, picks.tolist())
+
+    def _sampling_plan(self):
         mods = self.redundant_modules
         plan = getattr(self, '_sample_plan', None)
         if plan is None or plan[0] != len(mods):
@@ -306,30 +318,90 @@ class Net_Search(_NetBase):
                 groups.setdefault(m.n_choices, []).append(i)
             order = [i for k in groups for i in groups[k]]             # module index of every row of the stacked picks
             plan = self._sample_plan = (len(mods), groups, order)
-        _, groups, order = plan
+        return plan
+
+    def _draw_picks(self, group):
+        """Device side of the batched draw on the current stream: the per-node exponential_ calls in registration
+        order, one softmax + argmax per node width, the broadcast from rank 0.  Returns the picks in plan order."""
+        mods = self.redundant_modules
+        _, groups, order = self._sampling_plan()
         with torch.no_grad():
             dev = mods[0].alpha_prob.device
             qs = [torch.empty(m.n_choices, dtype=m.alpha_prob.dtype, device=dev).exponential_(1) for m in mods]
-            picks, onehots, gates = [], [], []
+            picks = []
             for k, idxs in groups.items():
                 probs = F.softmax(torch.stack([mods[i].alpha_prob.data for i in idxs]), dim=1)
-                pk = torch.argmax(probs / torch.stack([qs[i] for i in idxs]), dim=1)
-                picks.append(pk)
+                picks.append(torch.argmax(probs / torch.stack([qs[i] for i in idxs]), dim=1))
             picks = torch.cat(picks)                                   # in `order`
             if group is not False and torch.distributed.is_available() and torch.distributed.is_initialized() \
                     and torch.distributed.get_world_size(group) > 1:
                 torch.distributed.broadcast(picks, 0, group=group)
-            off = 0
+        return picks
+
+    def _apply_picks(self, picks, picks_list):
+        """One-hot gates on the device (current stream) and the host-side active / inactive bookkeeping."""
+        mods = self.redundant_modules
+        _, groups, order = self._sampling_plan()
+        with torch.no_grad():
+            off, onehots, gates = 0, [], []
             for k, idxs in groups.items():
                 oh = F.one_hot(picks[off:off + len(idxs)], k).to(mods[idxs[0]].alpha_gate.dtype)
                 off += len(idxs)
                 gates += [mods[i].alpha_gate.data for i in idxs]
                 onehots += list(oh.unbind(0))
             torch._foreach_copy_(gates, onehots)
-            for i, a in zip(order, picks.tolist()):
-                m = mods[i]
-                object.__setattr__(m, 'active_index', [a])             # plain attributes: skip nn.Module.__setattr__
-                object.__setattr__(m, 'inactive_index', [j for j in range(m.n_choices) if j != a])
+        for i, a in zip(order, picks_list):
+            m = mods[i]
+            object.__setattr__(m, 'active_index', [a])                 # plain attributes: skip nn.Module.__setattr__
+            object.__setattr__(m, 'inactive_index', [j for j in range(m.n_choices) if j != a])
+
+    # ---- drawing one step ahead -------------------------------------------------------------------------------------
+    # The picks have to reach the host before the step can be launched (they choose which kernels run), and a device ->
+    # host read at the top of a step drains the launch queue: the GPU idles while the host catches up.  The architecture
+    # parameters only change in the architecture step, so the NEXT step's draw can be issued as soon as this step is
+    # launched, on its own stream, ordered only after the last alpha update; by the time the next step starts the
+    # picks are already in pinned host memory.  Same generator, same calls, same order as drawing at the top of the step.
+    def alphas_updated(self):
+        """Called by the step harness right after the architecture optimizer's update was launched."""
+        dev = self.redundant_modules[0].alpha_prob.device
+        if dev.type == 'cuda':
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            self.__dict__['_alpha_event'] = ev
+
+    def _generator_state(self, dev):
+        return torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()].get_state()
+
+    def _alpha_versions(self):
+        return tuple((m.alpha_prob._version, m.alpha_prob.data_ptr()) for m in self.redundant_modules)
+
+    def presample(self, group=None):
+        dev = self.redundant_modules[0].alpha_prob.device
+        if dev.type != 'cuda':
+            return
+        st = self.__dict__.get('_sample_stream')
+        if st is None:
+            st = self.__dict__['_sample_stream'] = torch.cuda.Stream(device=dev)
+            n = len(self.redundant_modules)
+            self.__dict__['_picks_host'] = [torch.empty(n, dtype=torch.int64).pin_memory() for _ in range(2)]
+            self.__dict__['_picks_flip'] = 0
+        ev = self.__dict__.get('_alpha_event')
+        if ev is not None:
+            st.wait_event(ev)
+        self.__dict__['_picks_flip'] ^= 1
+        host = self.__dict__['_picks_host'][self.__dict__['_picks_flip']]
+        with torch.cuda.stream(st):
+            picks = self._draw_picks(group)
+            host.copy_(picks, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(st)
+        self.__dict__['_presampled'] = {'picks': picks, 'host': host, 'done': done, 'group': group,
+                                        'gen': self._generator_state(dev), 'alphas': self._alpha_versions()}
+
+    def _presample_valid(self, pre, group):
+        dev = pre['picks'].device
+        return (pre['group'] is group and pre['alphas'] == self._alpha_versions()
+                and torch.equal(pre['gen'], self._generator_state(dev)))
 
     def unused_modules_off(self):
         self._unused_modules = []

@@ -9,7 +9,7 @@ res = {}
 for (B, h, Nq, Nk, what) in [(64, 8, 100, 100, 'SA_y / RSA_y T'), (64, 8, 100, 14, 'GA_y T'), (64, 8, 14, 14, 'SA_x T'),
                              (64, 4, 100, 100, 'SA_y S'), (192, 8, 36, 36, 'SA_y I'), (192, 8, 36, 50, 'GA_y I'), (192, 8, 50, 50, 'SA_x I')]:
     I = h * 64
-    rel = what.startswith('SA_y / RSA')
+    rel = what.startswith('SA_y / RSA') and os.environ.get('ATT_BIAS', '1') == '1'
     sets = []
     for i in range(4):
         qkv = torch.randn(B * max(Nq, Nk), 3 * I, device=DEV).to(torch.bfloat16)
@@ -20,7 +20,7 @@ for (B, h, Nq, Nk, what) in [(64, 8, 100, 100, 'SA_y / RSA_y T'), (64, 8, 100, 1
         dbias = torch.empty_like(bias) if rel else None
         sets.append((qkv, o, do, dqkv, bias, dbias))
     kmask = torch.zeros(B, Nk, dtype=torch.uint8, device=DEV); kmask[:, Nk - 2:] = 1
-    drop = K.Drop(mmnas_b200.runtime.rng_state(DEV), 7, 0.1)
+    drop = K.Drop(mmnas_b200.runtime.rng_state(DEV), 7, 0.1) if os.environ.get('ATT_P', '0.1') != '0' else K.NO_DROP
     def fwd(s):
         qkv, o, do, dqkv, bias, dbias = s
         K.attn_fwd(B, h, Nq, Nk, qkv[:, 2 * I:].data_ptr(), 3 * I, qkv[:, I:].data_ptr(), 3 * I, qkv.data_ptr(), 3 * I, kmask, bias, o, I, 0.125, drop)
