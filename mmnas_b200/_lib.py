@@ -11,7 +11,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libmmnas_b200.so')
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 c_p, c_i, c_l, c_f, c_u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float, ctypes.c_ulonglong
 
@@ -41,6 +41,9 @@ SIGNATURES = {
     'mmnas_rng_advance': [c_p, c_p],
     'mmnas_rowmask_bf16': [c_p, c_p, c_i, c_i, c_p],
     'mmnas_box_geometry': [c_p, c_p, c_p, c_i, c_i, c_p],
+    'mmnas_lstm_workspace': [c_i, c_i, c_i, c_p],
+    'mmnas_lstm_fwd': [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p],
+    'mmnas_lstm_bwd': [c_i, c_i, c_i, c_p, c_p, c_p, c_p],
 }
 
 

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'lib', 'libmmnas_b200.so')
-SOURCES = ['elementwise.cu', 'gemm_simt.cu', 'gemm_tc.cu', 'layernorm.cu', 'attention.cu', 'attention_tc.cu', 'relbias.cu', 'relbias_mma.cu', 'blocks.cu', 'gemm_ln.cu']
+SOURCES = ['elementwise.cu', 'gemm_simt.cu', 'gemm_tc.cu', 'layernorm.cu', 'attention.cu', 'attention_tc.cu', 'relbias.cu', 'relbias_mma.cu', 'blocks.cu', 'gemm_ln.cu', 'lstm.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '--use_fast_math=false', '-Xcompiler', '-fPIC', '-shared', '-Xptxas', '-v']
 

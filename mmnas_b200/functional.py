@@ -877,6 +877,89 @@ class LinearFn(Function):
         return dx.reshape(shape), gW, gb, None, None, None
 
 
+class LSTMFn(Function):
+    """nn.LSTM(E -> H, one layer, batch_first, zero initial state), output sequence only (full_vqa.py:68-74,94-95),
+    bf16 arm.  The input projection of all steps is one tensor-core GEMM; the recurrence is ONE persistent cooperative
+    kernel per direction (csrc/lstm.cu) instead of cuDNN's two launches per step; weight / input gradients are GEMMs over
+    the saved gate gradients.  Buffers are sequence-major inside, the output batch-first as nn.LSTM returns it."""
+
+    @staticmethod
+    def forward(ctx, emb, w_ih, w_hh, b_ih, b_hh):
+        require_cuda(emb, w_ih, w_hh)
+        ctx.set_materialize_grads(False)
+        dev = emb.device
+        B, T, E = emb.shape
+        H = w_hh.shape[1]
+        Ep = _pad32(E)
+        TB = T * B
+        x16 = torch.zeros((TB, Ep), dtype=torch.bfloat16, device=dev) if Ep != E else torch.empty((TB, E), dtype=torch.bfloat16, device=dev)
+        x16.view(T, B, Ep)[:, :, :E].copy_(emb.detach().transpose(0, 1))
+        wih16 = torch.zeros((4 * H, Ep), dtype=torch.bfloat16, device=dev) if Ep != E else torch.empty((4 * H, E), dtype=torch.bfloat16, device=dev)
+        wih16[:, :E].copy_(w_ih.detach())
+        whh16 = K.cast_bf16(w_hh.detach())
+        bias = (b_ih.detach() + b_hh.detach()) if b_ih is not None else None
+        xw = torch.empty((TB, 4 * H), dtype=torch.float32, device=dev)
+        K.gemm_bf16(TB, 4 * H, Ep, x16, Ep, 0, wih16, Ep, 0, xw, 4 * H, bias=bias)
+        ws = torch.empty(K.lstm_workspace(T, B, H), dtype=torch.uint8, device=dev)
+        out = torch.empty((B, T, H), dtype=torch.float32, device=dev)
+        K.lstm_fwd(T, B, H, xw, whh16, out, None, ws)
+        whhT16 = w_hh.detach().t().to(torch.bfloat16).contiguous()      # [H, 4H]: the backward's register-resident operand
+        ctx.save_for_backward(x16, wih16, whhT16, ws)
+        ctx.meta = (T, B, E, Ep, H)
+        ctx.params = (w_ih, w_hh, b_ih, b_hh)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        if dout is None:
+            return (None,) * 5
+        T, B, E, Ep, H = ctx.meta
+        x16, wih16, whhT16, ws = ctx.saved_tensors
+        w_ih, w_hh, b_ih, b_hh = ctx.params
+        dev = dout.device
+        TB = T * B
+        K.lstm_bwd(T, B, H, dout.contiguous().float(), whhT16, ws)
+        al = lambda v: (v + 255) & ~255                      # workspace layout of csrc/lstm.cu
+        o_h16 = 0
+        o_dg = al((TB + B) * H * 2) + al(TB * 4 * H * 4) + al(TB * H * 4)
+        h16 = ws[o_h16:o_h16 + TB * H * 2].view(torch.bfloat16).view(TB, H)               # h_{t-1}, t = 0..T-1
+        dg = ws[o_dg:o_dg + TB * 4 * H * 2].view(torch.bfloat16).view(TB, 4 * H)
+        sinks = _direct((w_ih, w_hh, b_ih, b_hh)) if b_ih is not None else None
+        direct = sinks is not None and Ep == E
+        g_hh = sinks[1] if direct else torch.zeros_like(w_hh, dtype=torch.float32)
+        sk = _split_k(4 * H, H, TB)
+        K.gemm_bf16(4 * H, H, TB, dg, 4 * H, 1, h16, H, 1, g_hh, H, split_k=sk, accumulate=direct and sk == 1)
+        g_ihp = sinks[0] if direct else torch.zeros((4 * H, Ep), dtype=torch.float32, device=dev)
+        sk = _split_k(4 * H, Ep, TB)
+        K.gemm_bf16(4 * H, Ep, TB, dg, 4 * H, 1, x16, Ep, 1, g_ihp, Ep, split_k=sk, accumulate=direct and sk == 1)
+        g_b = None
+        if b_ih is not None:
+            if direct:
+                K.colsum(dg, TB, 4 * H, 4 * H, sinks[2], accumulate=True)
+                K.colsum(dg, TB, 4 * H, 4 * H, sinks[3], accumulate=True)
+            else:
+                g_b = torch.empty(4 * H, dtype=torch.float32, device=dev)
+                K.colsum(dg, TB, 4 * H, 4 * H, g_b)
+        dxp = torch.empty((TB, Ep), dtype=torch.float32, device=dev)
+        K.gemm_bf16(TB, Ep, 4 * H, dg, 4 * H, 0, wih16, Ep, 1, dxp, Ep)
+        demb = dxp.view(T, B, Ep)[:, :, :E].transpose(0, 1)
+        if direct:
+            runtime.notify_grads((w_ih, w_hh, b_ih, b_hh))
+            return demb, None, None, None, None
+        return demb, g_ihp[:, :E], g_hh, g_b, g_b
+
+
+def lstm(emb, mod):
+    """`mod(emb)[0]` for a one-layer batch_first nn.LSTM: the persistent kernels in the bf16 arm on CUDA, torch otherwise."""
+    H = mod.hidden_size
+    if (emb.is_cuda and runtime.get_precision() == 'bf16' and mod.num_layers == 1 and mod.batch_first
+            and not mod.bidirectional and mod.proj_size == 0 and H in (256, 512) and emb.shape[0] <= 256
+            and runtime.native_lstm):
+        return LSTMFn.apply(emb, mod.weight_ih_l0, mod.weight_hh_l0, mod.bias_ih_l0 if mod.bias else None,
+                            mod.bias_hh_l0 if mod.bias else None)
+    return mod(emb)[0]
+
+
 class AddLayerNormFn(Function):
     """LayerNorm(a + b) over the last dimension (full_vqa.py:107-108: proj_norm(attflat_x + attflat_y); full_vgd.py:108-109
     with a broadcast over the regions): the residual + LayerNorm kernel with `a` as the residual input."""

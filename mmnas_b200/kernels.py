@@ -1,5 +1,7 @@
 """Thin Python wrappers over the C ABI (one function per entry point).  They only translate torch tensors
 into raw pointers / pitches; no arithmetic happens here."""
+import ctypes
+
 import torch
 
 from . import _lib
@@ -142,6 +144,20 @@ def box_geometry(boxes, pad_mask):
 
 def rowmask_bf16(x16, mask, rows, cols):
     call('mmnas_rowmask_bf16', ptr(x16), ptr(mask), rows, cols, stream())
+
+
+def lstm_workspace(T, B, H):
+    n = ctypes.c_ulonglong(0)
+    call('mmnas_lstm_workspace', T, B, H, ctypes.addressof(n))
+    return int(n.value)
+
+
+def lstm_fwd(T, B, H, xw, whh16, out, out16, workspace):
+    call('mmnas_lstm_fwd', T, B, H, ptr(xw), ptr(whh16), ptr(out), ptr(out16), ptr(workspace), stream())
+
+
+def lstm_bwd(T, B, H, dout, whh16, workspace):
+    call('mmnas_lstm_bwd', T, B, H, ptr(dout), ptr(whh16), ptr(workspace), stream())
 
 
 def gemm_ln_bf16(M, N, K, A, lda, W, ldb, bias, x, gamma, beta, eps, z, out, out16, mean, sigma, drop=NO_DROP):

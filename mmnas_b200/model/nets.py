@@ -16,7 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import runtime
-from ..functional import StemImageFn
+from ..functional import StemImageFn, lstm
 from .mixed import MixedOp
 from .modules import AttFlat, LayerNorm, RelGeometry, linear
 from ..functional import AddLayerNormFn
@@ -127,7 +127,7 @@ class _NetBase(nn.Module):
         two padding masks, and the pairwise box geometry when the loader ships raw boxes."""
         frcn_feat, bbox_feat, y_rel, ques_ix, x_rel = input
         x_mask = make_mask(ques_ix.unsqueeze(2))
-        x_in, _ = self.lstm(self.embedding(ques_ix))
+        x_in = lstm(self.embedding(ques_ix), self.lstm)
         if self.BBOX_FEATURE:       # not used by any shipped config (BBOX_FEATURE = False, train_vqa.py:136): torch path
             y_mask = make_mask(frcn_feat)
             frcn_feat = torch.cat((frcn_feat, self.bboxfeat_linear(bbox_feat)), dim=-1)
@@ -200,7 +200,7 @@ class _NetBase(nn.Module):
         frcn_feat, bbox_feat, y_rel = images
         cap_ix, x_rel = captions
         x_mask_u = make_mask(cap_ix.unsqueeze(2))
-        x_u, _ = self.lstm(self.embedding(cap_ix))
+        x_u = lstm(self.embedding(cap_ix), self.lstm)
         y_u, y_mask_u = StemImageFn.apply(frcn_feat, self.imgfeat_linear.weight, self.imgfeat_linear.bias,
                                           runtime.get_precision())
         if y_rel.dim() == 3:

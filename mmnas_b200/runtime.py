@@ -12,6 +12,7 @@ _rng_states = {}
 shadows_fresh = False      # True while an engine step guarantees that the managed bf16 weight shadows are current
 direct_grads = False       # True while an engine step wants block backwards to accumulate straight into p.grad
 overlap_wgrad = os.environ.get('MMNAS_OVERLAP_WGRAD', '1') != '0'   # weight-gradient GEMMs on a side stream, concurrently with the dgrad / attention chain (env: ablation only)
+native_lstm = os.environ.get('MMNAS_NATIVE_LSTM', '1') != '0'      # persistent LSTM kernels in the bf16 arm (csrc/lstm.cu)
 compose_in_python = os.environ.get('MMNAS_COMPOSE_PY', '0') == '1'   # blocks composed from the primitive entry points in Python (one foreign call per kernel) instead of the block-level C calls: bench.py's per-kernel timing pass and the cross-check tests
 grad_listener = None       # callable(param): the data-parallel reducer's notification for directly written grads
 _salt_counter = itertools.count(1)

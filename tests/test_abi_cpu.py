@@ -28,7 +28,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     from mmnas_b200 import _lib
     lib = ctypes.CDLL(_lib.LIB_PATH)
     decl = declared()
-    assert len(decl) == 33            # 19 primitive entry points + 10 block-level ones (ABI v7)
+    assert len(decl) == 36            # 22 primitive entry points + 10 block-level ones + 4 queries (ABI v8)
     for name in decl:
         assert hasattr(lib, name), name
     lib.mmnas_abi_version.restype = ctypes.c_int

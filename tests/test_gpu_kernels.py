@@ -592,3 +592,34 @@ def test_fused_gemm_layernorm_matches_the_two_kernel_tail(M, N, K, variant):
     assert normwise(out, out_ref) < 2e-6
     assert normwise(out16.float(), out16_ref.float()) < 8e-3   # one bf16 ulp where the fp32 values straddle a rounding boundary
     assert (out16 != out16_ref).float().mean() < 1e-3
+
+
+# ------------------------------------------------------------------------------------------ text stem: LSTM
+@pytest.mark.parametrize('B,T,E,H', [(64, 14, 300, 512), (192, 50, 300, 512), (64, 14, 300, 256), (5, 3, 40, 256), (33, 7, 300, 512), (130, 5, 64, 512), (8, 1, 300, 512)])
+def test_native_lstm_matches_torch_lstm(B, T, E, H):
+    """functional.LSTMFn (one GEMM for the input projection, one persistent cooperative kernel for the recurrence per
+    direction, csrc/lstm.cu) against torch.nn.LSTM in float64: output sequence and every gradient (embedded input,
+    W_ih, W_hh, both biases) within the bf16 arm's tolerance (full_vqa.py:68-74,94-95)."""
+    import mmnas_b200
+    from mmnas_b200.functional import LSTMFn
+    torch.manual_seed(7)
+    ref = torch.nn.LSTM(E, H, num_layers=1, batch_first=True).double()
+    emb = torch.randn(B, T, E, dtype=torch.float64) * 0.5
+    emb.requires_grad_(True)
+    go = torch.randn(B, T, H, dtype=torch.float64)
+    out_ref, _ = ref(emb)
+    (out_ref * go).sum().backward()
+    params = [p.detach().float().to(DEV).requires_grad_(True) for p in (ref.weight_ih_l0, ref.weight_hh_l0, ref.bias_ih_l0, ref.bias_hh_l0)]
+    e32 = emb.detach().float().to(DEV).requires_grad_(True)
+    with mmnas_b200.precision('bf16'):
+        out = LSTMFn.apply(e32, *params)
+        (out * go.float().to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    assert normwise(out, out_ref) < 1e-2
+    assert normwise(e32.grad, emb.grad) < 2e-2
+    for p, q in zip(params, (ref.weight_ih_l0, ref.weight_hh_l0, ref.bias_ih_l0, ref.bias_hh_l0)):
+        assert normwise(p.grad, q.grad) < 2e-2
+    # same inputs -> same bits (no atomics on the recurrent path)
+    with mmnas_b200.precision('bf16'), torch.no_grad():
+        out2 = LSTMFn.apply(e32, *params)
+    assert torch.equal(out.detach(), out2)
