@@ -135,18 +135,18 @@ int mmnas_box_geometry(const float* boxes, const unsigned char* pad_mask, float*
  * The caller computes the input projection of all steps, xw [T*B, 4H] fp32 = X W_ih^T + b_ih + b_hh with rows in
  * sequence-major order (t*B + b) and torch's gate order (i, f, g, o), e.g. with mmnas_gemm_bf16.  mmnas_lstm_fwd runs the
  * T dependent steps in ONE kernel: clusters of 16 CTAs own 16 or 32 batch rows each, W_hh [4H, H] bf16 stays in registers
- * as mma.sync fragments, h_t is exchanged through distributed shared memory with one cluster barrier per step.  Writes
+ * as mma.sync fragments, h_t is exchanged through distributed shared memory (st.async on the receiver's mbarrier).  Writes
  * out [B, T, H] fp32 batch-first (+ optional bf16 copy out16 [B*T, H]).
  * The workspace (mmnas_lstm_workspace bytes, 256-byte aligned, untouched between forward and backward) keeps, in this
  * order: h16 [(T+1)*B, H] bf16 (slice 0 zero, slice t+1 = h_t), activated gates [T*B, 4H] fp32, cell states [T*B, H]
- * fp32, dG [T*B, 4H] bf16.  mmnas_lstm_bwd takes dout [B, T, H] fp32 and the TRANSPOSED weights W_hh^T [H, 4H] bf16 and
+ * fp32, dG [T*B, 4H] bf16.  mmnas_lstm_bwd takes dout [B, T, H] fp32 and the same W_hh [4H, H] bf16 and
  * fills dG (gradients of the gate pre-activations, sequence-major); the caller finishes with dW_hh = dG^T h16[0:T*B],
  * dW_ih = dG^T X, db_ih = db_hh = colsum(dG), dX = dG W_ih.  1 <= B <= 256; H must be 256 or 512, otherwise
  * MMNAS_ERR_UNSUPPORTED (-2; also when the device cannot schedule a 16-CTA cluster) and the caller keeps its own LSTM. */
 int mmnas_lstm_workspace(int T, int B, int H, unsigned long long* bytes);
 int mmnas_lstm_fwd(int T, int B, int H, const float* xw, const void* whh_bf16, float* out, void* out_bf16, void* workspace,
                    mmnas_stream stream);
-int mmnas_lstm_bwd(int T, int B, int H, const float* dout, const void* whhT_bf16, void* workspace, mmnas_stream stream);
+int mmnas_lstm_bwd(int T, int B, int H, const float* dout, const void* whh_bf16, void* workspace, mmnas_stream stream);
 
 /* ---- optimizer tail: clip_grad_norm_ (train_vqa.py:310) + Adam (train_vqa.py:311 via optimizer.py:14-20) ------
  * out[0] = sum(x^2) over a flat fp32 buffer (n % 4 == 0).  Bit-reproducible (fixed summation order, no float

@@ -36,7 +36,7 @@ constexpr int THREADS = 256;          // 8 warps
 struct LstmArgs {
   int T, B, H, R;                // R = batch rows per cluster (16 or 32)
   const float* xw;               // [T*B, 4H]  input projection + both biases (sequence-major rows t*B + b)
-  const __nv_bfloat16* whh;      // fwd: W_hh [4H, H];  bwd: W_hh^T [H, 4H]
+  const __nv_bfloat16* whh;      // W_hh [4H, H]
   float* out;                    // [B, T, H]  fp32, batch-first
   __nv_bfloat16* out16;          // [B*T, H]   bf16 shadow of out (or null)
   __nv_bfloat16* h16;            // [(T+1)*B, H]  slice 0 = zeros, slice t+1 = h_t
@@ -300,16 +300,21 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_bwd_kernel(LstmArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
 
-  // weight fragments from W_hh^T [H, 4H]: n-tile j of this warp = units n0 .. n0 + 7, n0 = warp H/8 + 8j (column g = unit
-  // n0 + g); k chunk c covers local k = 32c .. 32c + 31 = gate q = 32c / UPC, own units (32c % UPC) ..
+  // weight fragments straight from W_hh [4H, H]: n-tile j of this warp = units n0 .. n0 + 7, n0 = warp H/8 + 8j (column g =
+  // unit n0 + g); k chunk c covers local k = 32c .. 32c + 31, i.e. gate q = 32c / UPC, own units (32c % UPC) .. — eight
+  // 2-byte loads a fragment register pair, once per launch (1 MB of weights, L2-resident)
   uint4 wreg[NTW][KCB];
 #pragma unroll
   for (int j = 0; j < NTW; ++j) {
-    const __nv_bfloat16* wrow = a.whh + (size_t)(warp * (H / 8) + 8 * j + g) * K4 + u0;
+    const unsigned short* wcol = reinterpret_cast<const unsigned short*>(a.whh) + warp * (H / 8) + 8 * j + g;
 #pragma unroll
     for (int c = 0; c < KCB; ++c) {
       const int kl = 32 * c + 8 * t4, q = kl / UPC, ul = kl % UPC;
-      wreg[j][c] = __ldg(reinterpret_cast<const uint4*>(wrow + q * H + ul));
+      const unsigned short* w0 = wcol + (size_t)(q * H + u0 + ul) * H;
+      uint32_t e[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) e[i] = __ldg(w0 + (size_t)i * H);
+      wreg[j][c] = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
     }
   }
   float dcr[PP];
@@ -463,12 +468,12 @@ extern "C" int mmnas_lstm_fwd(int T, int B, int H, const float* xw, const void* 
   return launch_cluster(lstm_fwd_kernel<1>, smem, a, (cudaStream_t)stream);
 }
 
-extern "C" int mmnas_lstm_bwd(int T, int B, int H, const float* dout, const void* whhT16, void* workspace,
+extern "C" int mmnas_lstm_bwd(int T, int B, int H, const float* dout, const void* whh16, void* workspace,
                               mmnas_stream stream) {
   if (int rc = check(T, B, H)) return rc;
-  MMNAS_CHECK_ARG(dout && whhT16 && workspace, "lstm_bwd: null pointer");
+  MMNAS_CHECK_ARG(dout && whh16 && workspace, "lstm_bwd: null pointer");
   LstmArgs a = {};
-  a.T = T; a.B = B; a.H = H; a.R = rows_per_cluster(B); a.dout = dout; a.whh = static_cast<const __nv_bfloat16*>(whhT16);
+  a.T = T; a.B = B; a.H = H; a.R = rows_per_cluster(B); a.dout = dout; a.whh = static_cast<const __nv_bfloat16*>(whh16);
   carve(a, workspace);
   const int upc = H / CL;
   // dG slice rows | partial dh [2][16][R][upc] fp32 | saved gates [R][4][upc] | c_t, c_{t-1}, dout [R][upc] | 2 mbarriers

@@ -879,9 +879,10 @@ class LinearFn(Function):
 
 class LSTMFn(Function):
     """nn.LSTM(E -> H, one layer, batch_first, zero initial state), output sequence only (full_vqa.py:68-74,94-95),
-    bf16 arm.  The input projection of all steps is one tensor-core GEMM; the recurrence is ONE persistent cooperative
-    kernel per direction (csrc/lstm.cu) instead of cuDNN's two launches per step; weight / input gradients are GEMMs over
-    the saved gate gradients.  Buffers are sequence-major inside, the output batch-first as nn.LSTM returns it."""
+    bf16 arm.  The input projection of all steps is one tensor-core GEMM; the recurrence is ONE kernel per direction
+    (csrc/lstm.cu) instead of cuDNN's two launches per step; weight / input gradients are GEMMs over the saved gate
+    gradients, the weight-gradient ones on the side stream next to the input-gradient one.  Buffers are sequence-major
+    inside, the output batch-first as nn.LSTM returns it (with its bf16 copy attached for the first encoder block)."""
 
     @staticmethod
     def forward(ctx, emb, w_ih, w_hh, b_ih, b_hh):
@@ -902,9 +903,10 @@ class LSTMFn(Function):
         K.gemm_bf16(TB, 4 * H, Ep, x16, Ep, 0, wih16, Ep, 0, xw, 4 * H, bias=bias)
         ws = torch.empty(K.lstm_workspace(T, B, H), dtype=torch.uint8, device=dev)
         out = torch.empty((B, T, H), dtype=torch.float32, device=dev)
-        K.lstm_fwd(T, B, H, xw, whh16, out, None, ws)
-        whhT16 = w_hh.detach().t().to(torch.bfloat16).contiguous()      # [H, 4H]: the backward's register-resident operand
-        ctx.save_for_backward(x16, wih16, whhT16, ws)
+        out16 = torch.empty((B, T, H), dtype=torch.bfloat16, device=dev)
+        K.lstm_fwd(T, B, H, xw, whh16, out, out16, ws)
+        out._mmnas_bf16 = out16
+        ctx.save_for_backward(x16, wih16, whh16, ws)
         ctx.meta = (T, B, E, Ep, H)
         ctx.params = (w_ih, w_hh, b_ih, b_hh)
         return out
@@ -914,39 +916,41 @@ class LSTMFn(Function):
         if dout is None:
             return (None,) * 5
         T, B, E, Ep, H = ctx.meta
-        x16, wih16, whhT16, ws = ctx.saved_tensors
+        x16, wih16, whh16, ws = ctx.saved_tensors
         w_ih, w_hh, b_ih, b_hh = ctx.params
         dev = dout.device
         TB = T * B
-        K.lstm_bwd(T, B, H, dout.contiguous().float(), whhT16, ws)
+        K.lstm_bwd(T, B, H, dout.contiguous().float(), whh16, ws)
         al = lambda v: (v + 255) & ~255                      # workspace layout of csrc/lstm.cu
-        o_h16 = 0
         o_dg = al((TB + B) * H * 2) + al(TB * 4 * H * 4) + al(TB * H * 4)
-        h16 = ws[o_h16:o_h16 + TB * H * 2].view(torch.bfloat16).view(TB, H)               # h_{t-1}, t = 0..T-1
+        h16 = ws[:TB * H * 2].view(torch.bfloat16).view(TB, H)                            # h_{t-1}, t = 0..T-1
         dg = ws[o_dg:o_dg + TB * 4 * H * 2].view(torch.bfloat16).view(TB, 4 * H)
-        sinks = _direct((w_ih, w_hh, b_ih, b_hh)) if b_ih is not None else None
-        direct = sinks is not None and Ep == E
-        g_hh = sinks[1] if direct else torch.zeros_like(w_hh, dtype=torch.float32)
-        sk = _split_k(4 * H, H, TB)
-        K.gemm_bf16(4 * H, H, TB, dg, 4 * H, 1, h16, H, 1, g_hh, H, split_k=sk, accumulate=direct and sk == 1)
-        g_ihp = sinks[0] if direct else torch.zeros((4 * H, Ep), dtype=torch.float32, device=dev)
-        sk = _split_k(4 * H, Ep, TB)
-        K.gemm_bf16(4 * H, Ep, TB, dg, 4 * H, 1, x16, Ep, 1, g_ihp, Ep, split_k=sk, accumulate=direct and sk == 1)
-        g_b = None
-        if b_ih is not None:
-            if direct:
-                K.colsum(dg, TB, 4 * H, 4 * H, sinks[2], accumulate=True)
-                K.colsum(dg, TB, 4 * H, 4 * H, sinks[3], accumulate=True)
-            else:
-                g_b = torch.empty(4 * H, dtype=torch.float32, device=dev)
-                K.colsum(dg, TB, 4 * H, 4 * H, g_b)
+        hh, bb = _Sink((w_hh,), dev), (_Sink((b_ih,), dev), _Sink((b_hh,), dev)) if b_ih is not None else ()
+        ih = _Sink((w_ih,), dev) if Ep == E else None
+        # destinations first, on the main stream: inside `with fork` only the library's launches move to the side stream
+        sk_hh, sk_ih = _split_k(4 * H, H, TB), _split_k(4 * H, Ep, TB)
+        hh.prepare(zero=sk_hh > 1)
+        if ih is not None:
+            ih.prepare(zero=sk_ih > 1)
+            g_ih = ih.buf
+        else:
+            g_ih = (torch.zeros if sk_ih > 1 else torch.empty)((4 * H, Ep), dtype=torch.float32, device=dev)
+        for sink in bb:
+            sink.prepare(zero=False)
+        fork = _Fork(dev, True)
+        with fork:                                           # weight gradients next to the input-gradient GEMM
+            K.gemm_bf16(4 * H, H, TB, dg, 4 * H, 1, h16, H, 1, hh.buf, H, split_k=sk_hh, accumulate=hh.direct and sk_hh == 1)
+            K.gemm_bf16(4 * H, Ep, TB, dg, 4 * H, 1, x16, Ep, 1, g_ih, Ep, split_k=sk_ih,
+                        accumulate=ih is not None and ih.direct and sk_ih == 1)
+            for sink in bb:
+                K.colsum(dg, TB, 4 * H, 4 * H, sink.buf, accumulate=sink.direct)
         dxp = torch.empty((TB, Ep), dtype=torch.float32, device=dev)
         K.gemm_bf16(TB, Ep, 4 * H, dg, 4 * H, 0, wih16, Ep, 1, dxp, Ep)
         demb = dxp.view(T, B, Ep)[:, :, :E].transpose(0, 1)
-        if direct:
-            runtime.notify_grads((w_ih, w_hh, b_ih, b_hh))
-            return demb, None, None, None, None
-        return demb, g_ihp[:, :E], g_hh, g_b, g_b
+        fork.join()
+        g_w_ih = ih.grads()[0] if ih is not None else g_ih[:, :E]
+        g_b = tuple(sink.grads()[0] for sink in bb) if bb else (None, None)
+        return demb, g_w_ih, hh.grads()[0], g_b[0], g_b[1]
 
 
 def lstm(emb, mod):
