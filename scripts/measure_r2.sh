@@ -33,4 +33,6 @@ timeout 300 python scripts/bench_ops.py gpurun_out/${TAG}_ops_roofline.json > gp
 timeout 300 python scripts/bench_gemm_pair.py > gpurun_out/${TAG}_gemm_shapes.txt 2>&1
 timeout 300 python scripts/bench_gemm.py 2>&1 | grep cublas > gpurun_out/${TAG}_gemm_cublas.txt
 timeout 300 python scripts/bench_mining.py gpurun_out/${TAG}_itm_mining.json 2>&1 | tail -3
+timeout 300 python scripts/bench_lstm.py > gpurun_out/${TAG}_lstm.txt 2>&1; tail -4 gpurun_out/${TAG}_lstm.txt
+timeout 300 python scripts/bench_gemm_bn64.py > gpurun_out/${TAG}_gemm_bn64.txt 2>&1
 ls gpurun_out | grep "^${TAG}_" | tr '\n' ' '
