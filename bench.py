@@ -260,6 +260,8 @@ def kernel_table(records):
     """Aggregate the live CUDA-event records per kernel family with algorithmic FLOPs / bytes."""
     fam = {}
     for name, a, ms in records:
+        if name.endswith('_workspace') or name.endswith('_sizeof'):
+            continue                    # size queries: foreign calls, not kernels
         flops = byts = 0.0
         key = name.replace('mmnas_', '')
         if name == 'mmnas_gemm_bf16':
@@ -338,11 +340,13 @@ def run_workloads(args, world, rank, dev, barrier):
                        alpha_betas=cfg.ALPHA_OPT_BETAS, mode=cfg.ALPHA_BINARY_MODE)
     tw, lw, nw = timed(lambda: sstep.weight_step(*train_b), steps)
     ta, la, na = timed(lambda: sstep.arch_step(*eval_b), steps)
+    nw, na = nw + sstep.replayed_launches(False), na + sstep.replayed_launches(True)     # eager block calls + graph segments
     every = cfg.ALPHA_EVERY
     out['search_vqa'] = {
         'config': 'BASELINE configs[2]: MMnas-VQA supernet search step, H=256, 4 heads, MixedOp over SA/FFN (12 enc nodes) '
-                  'and SA/RSA/GA/FFN (18 dec nodes), batch 64 per GPU, dropout 0.1, eager launches (the sampled path '
-                  'changes every step), seed-888 sampling with the reference\'s RNG consumption',
+                  'and SA/RSA/GA/FFN (18 dec nodes), batch 64 per GPU, dropout 0.1; the sampled backbone is launched eagerly '
+                  '(one foreign call per block), stem / heads + loss / stem backward / clip + Adam replay from four CUDA '
+                  'graphs; seed-888 sampling with the reference\'s RNG consumption, drawn one step ahead',
         'weight_step': {'ms_per_step': tw, 'samples_per_s': BATCH * world / (tw / 1e3), 'launches_per_step': nw,
                         'final_loss': lw},
         'arch_step': {'ms_per_step': ta, 'samples_per_s': BATCH * world / (ta / 1e3), 'launches_per_step': na,

@@ -479,7 +479,7 @@ class TrainStep:
 class _Segments:
     """State of SearchStep's segmented replay: static inputs, the tensors handed from one segment to the next, the four
     captured graphs."""
-    key = ex_key = inputs = target = x_in = y_in = x_mask = y_mask = x_out = y_out = loss = graphs = None
+    key = ex_key = inputs = target = x_in = y_in = x_mask = y_mask = x_out = y_out = loss = graphs = graph_launches = None
 
 
 class SearchStep:
@@ -609,12 +609,15 @@ class SearchStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         pool = torch.cuda.graph_pool_handle()
-        seg.graphs = []
+        seg.graphs, seg.graph_launches = [], []
+        from . import _lib
         for body in (self._seg_a, self._seg_b, self._seg_c, self._seg_d):
             g = torch.cuda.CUDAGraph()
+            l0 = _lib.launches()
             with torch.cuda.graph(g, pool=pool):
                 body(seg)
             seg.graphs.append(g)
+            seg.graph_launches.append(_lib.launches() - l0)      # library kernels inside this graph (replayed, not re-counted)
         seg.ex_key = ex.key
         with torch.no_grad():
             for t, v in zip(state, saved):
@@ -648,6 +651,13 @@ class SearchStep:
             runtime.shadows_fresh = False
             runtime.direct_grads, runtime.grad_listener = False, None
         return seg.loss.clone()
+
+    def replayed_launches(self, arch=False):
+        """Library kernels a step replays from its captured segments (not seen by the library's launch counter)."""
+        if self._seg is None:
+            return 0
+        n = self._seg.graph_launches
+        return sum(n[:3]) + (0 if arch else n[3])
 
     def _off(self):
         # Net_Search.unused_modules_off/back (hygr_vqa.py:175-196) swap the candidates that do not run for None; the

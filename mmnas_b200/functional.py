@@ -86,7 +86,13 @@ class _Fork:
     """Weight-gradient work of one block backward on the side stream: `with fork:` enqueues there after everything
     issued so far on the main stream; join() makes the main stream wait for it (called before the backward returns,
     so every buffer the side work touches is still referenced and later reuse of its memory is ordered after it).
-    Captured in a CUDA graph this becomes a parallel branch; SMs left idle by a 100-CTA dgrad GEMM run wgrad CTAs."""
+    Captured in a CUDA graph this becomes a parallel branch; SMs left idle by a 100-CTA dgrad GEMM run wgrad CTAs.
+
+    INVARIANT: inside `with fork:` only the library's launches move to the side stream — torch's current stream and the
+    caching allocator still see the main stream.  No torch kernel may be issued there: a `torch.zeros` destination
+    filled on the main stream races the side-stream kernel that accumulates into it.  Prepare every destination
+    (`_Sink.prepare`, temporaries) BEFORE entering the block; `_Sink.prepare` raises if it is called inside one."""
+    depth = 0
 
     def __init__(self, dev, enabled):
         self.enabled = enabled and runtime.overlap_wgrad
@@ -104,10 +110,12 @@ class _Fork:
             else:
                 _lib.set_stream_override(self.side.cuda_stream)
             self.used = True
+            _Fork.depth += 1
         return self
 
     def __exit__(self, *a):
         if self.enabled:
+            _Fork.depth -= 1
             if _FORK_CTX:
                 self.ctx.__exit__(*a)
             else:
@@ -131,6 +139,9 @@ class _Sink:
         self.buf = self.target
 
     def prepare(self, zero):
+        if _Fork.depth and not _FORK_CTX:
+            raise RuntimeError('_Sink.prepare() inside `with fork:`: the fill would run on the main stream and race the '
+                               'side-stream kernels (see _Fork)')
         if not self.direct:
             rows = sum(p.shape[0] for p in self.params)
             shape = (rows,) + tuple(self.params[0].shape[1:])
