@@ -965,13 +965,22 @@ class LSTMFn(Function):
 
 
 def lstm(emb, mod):
-    """`mod(emb)[0]` for a one-layer batch_first nn.LSTM: the persistent kernels in the bf16 arm on CUDA, torch otherwise."""
+    """`mod(emb)[0]` for a one-layer batch_first nn.LSTM: the cluster kernels of csrc/lstm.cu in the bf16 arm on CUDA
+    (H = 256 / 512, at most 256 rows), torch's LSTM otherwise — the fp32 parity arm, other shapes, and devices that
+    cannot schedule a 16-CTA cluster (the library reports MMNAS_ERR_UNSUPPORTED; said once, then torch's LSTM is used)."""
     H = mod.hidden_size
     if (emb.is_cuda and runtime.get_precision() == 'bf16' and mod.num_layers == 1 and mod.batch_first
             and not mod.bidirectional and mod.proj_size == 0 and H in (256, 512) and emb.shape[0] <= 256
             and runtime.native_lstm):
-        return LSTMFn.apply(emb, mod.weight_ih_l0, mod.weight_hh_l0, mod.bias_ih_l0 if mod.bias else None,
-                            mod.bias_hh_l0 if mod.bias else None)
+        try:
+            return LSTMFn.apply(emb, mod.weight_ih_l0, mod.weight_hh_l0, mod.bias_ih_l0 if mod.bias else None,
+                                mod.bias_hh_l0 if mod.bias else None)
+        except _lib.MMnasLibraryError as e:
+            if '(-2)' not in str(e):
+                raise
+            import warnings
+            warnings.warn('mmnas_b200: LSTM kernels unsupported on this device (%s); using torch.nn.LSTM' % e)
+            runtime.native_lstm = False
     return mod(emb)[0]
 
 
