@@ -296,11 +296,11 @@ int check_common(int dtype, int B, int heads, int Nq, int Nk, int head_dim) {
 // tensor-core implementations (attention_tc.cu); MMNAS_ERR_UNSUPPORTED = operands miss the TMA constraints
 int mmnas_attn_fwd_tc(int B, int heads, int Nq, int Nk, const void* q, long ldq, const void* k, long ldk, const void* v,
                       long ldv, const unsigned char* kmask, const float* bias, void* o, long ldo, float scale,
-                      const unsigned long long* rng_state, unsigned long long salt, float p, cudaStream_t s, int bias_il);
+                      const unsigned long long* rng_state, unsigned long long salt, float p, cudaStream_t s);
 int mmnas_attn_bwd_tc(int B, int heads, int Nq, int Nk, const void* q, long ldq, const void* k, long ldk, const void* v,
                       long ldv, const unsigned char* kmask, const float* bias, const void* o, long ldo, const void* dout,
                       long lddo, void* dq, long lddq, void* dk, long lddk, void* dv, long lddv, float* dbias, float scale,
-                      const unsigned long long* rng_state, unsigned long long salt, float p, cudaStream_t s, int bias_il);
+                      const unsigned long long* rng_state, unsigned long long salt, float p, cudaStream_t s);
 
 // tuning only (MMNAS_ATTN_TC_MIN_NK): key counts below this take the FFMA kernel in the bf16 arm too
 static int tc_min_nk() {
@@ -319,7 +319,7 @@ extern "C" int mmnas_attn_fwd(int dtype, int B, int heads, int Nq, int Nk, int h
   MMNAS_CHECK_ARG(q && k && v && o, "attn_fwd: null operand");
   if (dtype == 1 && Nk >= tc_min_nk()) {   // bf16 arm: tcgen05 kernel; the FFMA kernel below only if TMA cannot address the operands
     rc = mmnas_attn_fwd_tc(B, heads, Nq, Nk, q, ldq, k, ldk, v, ldv, kmask, bias, o, ldo, scale, rng_state, salt, p,
-                           (cudaStream_t)stream, 0);
+                           (cudaStream_t)stream);
     if (rc != MMNAS_ERR_UNSUPPORTED) return rc;
   }
   size_t smem = fwd_smem(Nq, Nk);
@@ -355,7 +355,7 @@ extern "C" int mmnas_attn_bwd(int dtype, int B, int heads, int Nq, int Nk, int h
   MMNAS_CHECK_ARG(q && k && v && o && dout && dq && dk && dv, "attn_bwd: null operand");
   if (dtype == 1 && Nk >= tc_min_nk()) {
     rc = mmnas_attn_bwd_tc(B, heads, Nq, Nk, q, ldq, k, ldk, v, ldv, kmask, bias, o, ldo, dout, lddo, dq, lddq, dk, lddk,
-                           dv, lddv, dbias, scale, rng_state, salt, p, (cudaStream_t)stream, 0);
+                           dv, lddv, dbias, scale, rng_state, salt, p, (cudaStream_t)stream);
     if (rc != MMNAS_ERR_UNSUPPORTED) return rc;
   }
   size_t smem = bwd_smem(Nq, Nk);

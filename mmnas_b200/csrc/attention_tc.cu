@@ -35,7 +35,6 @@ struct AttnTcArgs {
   const __nv_bfloat16* dout; long lddo;
   __nv_bfloat16 *dq, *dk, *dv; long lddq, lddk, lddv;
   float* dbias;
-  int bias_il;               // bias / dbias planes in the row-interleaved layout (see bias_ptr): block-level calls only
 };
 
 // byte offset of element (row, col) in a [128 x 128] bf16 tile stored as two K-major SW128 chunks
@@ -52,10 +51,8 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // Row-resident softmax state of one thread (= one query row = one TMEM lane): up to 4 chunks of 32 logits.
 struct RowCtx {
   uint32_t mk0, mk1, mk2, mk3;   // padded-key bitmask, bit t of word c = key 32c+t (warp-uniform)
-  const float* brow;       // bias of (row, key 0) or null
+  const float* brow;       // bias row or null
   uint64_t rowbase;        // dropout element index of (row, key 0)
-  long bofs;               // offset of (row, key 0) inside bias / dbias
-  int gstride;             // distance (floats) between the 4-key groups of a row: 4, or 4 Nq in the interleaved layout
 };
 
 __device__ __forceinline__ RowCtx make_row_ctx(const AttnTcArgs& a, int b, int h, int i, bool row_ok, int lane) {
@@ -70,12 +67,7 @@ __device__ __forceinline__ RowCtx make_row_ctx(const AttnTcArgs& a, int b, int h
   }
   c.mk0 = mk[0]; c.mk1 = mk[1]; c.mk2 = mk[2]; c.mk3 = mk[3];
   c.rowbase = (((uint64_t)b * a.heads + h) * a.Nq + i) * a.Nk;
-  // Natural layout: [B, heads, Nq, Nk].  Row-interleaved (bias_il, Nk % 4 == 0): inside a (b, h) plane the element (i, j)
-  // sits at ((j / 4) Nq + i) 4 + j % 4, so the 16-byte reads of the 32 rows of a warp are one contiguous 512-byte run
-  // instead of 32 separate lines (thread i owns query row i).  The relation-bias kernels write / read the same layout.
-  c.bofs = a.bias_il ? (long)(((uint64_t)b * a.heads + h) * a.Nq * a.Nk) + 4 * i : (long)c.rowbase;
-  c.gstride = a.bias_il ? 4 * a.Nq : 4;
-  c.brow = (a.bias && row_ok) ? a.bias + c.bofs : nullptr;
+  c.brow = (a.bias && row_ok) ? a.bias + c.rowbase : nullptr;
   return c;
 }
 
@@ -95,7 +87,7 @@ __device__ __forceinline__ void chunk_bias(const AttnTcArgs& a, const RowCtx& c,
 #pragma unroll
       for (int g = 0; g < 8; ++g)
         if (j0 + 4 * g < a.Nk) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(c.brow + (long)((j0 >> 2) + g) * c.gstride));
+          const float4 v = __ldg(reinterpret_cast<const float4*>(c.brow + j0) + g);
           bb[4 * g] = v.x; bb[4 * g + 1] = v.y; bb[4 * g + 2] = v.z; bb[4 * g + 3] = v.w;
         }
     } else {
@@ -374,7 +366,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   const float mxl = mx * LOG2E;
   const float inv = (row_ok && sum > 0.f) ? 1.f / sum : 0.f;     // rows >= Nq contribute zeros to dK / dV
   const float delta = num * inv;
-  float* dbrow = (a.dbias && row_ok) ? a.dbias + ctx.bofs : nullptr;
+  float* dbrow = (a.dbias && row_ok) ? a.dbias + ctx.rowbase : nullptr;
 #pragma unroll 1
   for (int cc = 0; cc < NC; ++cc) {                 // pass 2: P (dropped), dS -> shared memory; d bias -> global
     uint32_t r[32], rp[32];
@@ -403,7 +395,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       }
       if (dbrow && cc * 32 + 4 * g < Nk) {
         if (VEC) {
-          *reinterpret_cast<float4*>(dbrow + (long)(cc * 8 + g) * ctx.gstride) = make_float4(ds[4 * g], ds[4 * g + 1], ds[4 * g + 2], ds[4 * g + 3]);
+          *reinterpret_cast<float4*>(dbrow + cc * 32 + 4 * g) = make_float4(ds[4 * g], ds[4 * g + 1], ds[4 * g + 2], ds[4 * g + 3]);
         } else {
 #pragma unroll
           for (int u = 0; u < 4; ++u)
@@ -489,10 +481,9 @@ bool aligned16(const void* p, long ld) { return ((uintptr_t)p % 16) == 0 && (ld 
 // Returns MMNAS_ERR_UNSUPPORTED when the operands do not meet the TMA constraints (caller then uses the FFMA kernel).
 int mmnas_attn_fwd_tc(int B, int heads, int Nq, int Nk, const void* q, long ldq, const void* k, long ldk, const void* v,
                       long ldv, const unsigned char* kmask, const float* bias, void* o, long ldo, float scale,
-                      const unsigned long long* rng_state, unsigned long long salt, float p, cudaStream_t s, int bias_il) {
+                      const unsigned long long* rng_state, unsigned long long salt, float p, cudaStream_t s) {
   if (Nq > 128 || Nk > 128 || !aligned16(q, ldq) || !aligned16(k, ldk) || !aligned16(v, ldv) || !aligned16(o, ldo))
     return MMNAS_ERR_UNSUPPORTED;
-  if (bias_il && (Nk & 3)) return MMNAS_ERR_UNSUPPORTED;
   CUtensorMap tq, tk, tv;
   int rc;
   if ((rc = encode_2d(&tq, q, heads * 64, (long)B * Nq, ldq, 64, 128))) return rc;
@@ -501,7 +492,6 @@ int mmnas_attn_fwd_tc(int B, int heads, int Nq, int Nk, const void* q, long ldq,
   AttnTcArgs a = {};
   a.B = B; a.heads = heads; a.Nq = Nq; a.Nk = Nk; a.kmask = kmask; a.bias = bias;
   a.o = (__nv_bfloat16*)o; a.ldo = ldo; a.scale = scale; a.drop = mk_drop(rng_state, salt, p);
-  a.bias_il = bias_il;
   static bool attr_done = false;
   if (!attr_done) {
     MMNAS_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
@@ -516,11 +506,10 @@ int mmnas_attn_fwd_tc(int B, int heads, int Nq, int Nk, const void* q, long ldq,
 int mmnas_attn_bwd_tc(int B, int heads, int Nq, int Nk, const void* q, long ldq, const void* k, long ldk, const void* v,
                       long ldv, const unsigned char* kmask, const float* bias, const void* o, long ldo, const void* dout,
                       long lddo, void* dq, long lddq, void* dk, long lddk, void* dv, long lddv, float* dbias, float scale,
-                      const unsigned long long* rng_state, unsigned long long salt, float p, cudaStream_t s, int bias_il) {
+                      const unsigned long long* rng_state, unsigned long long salt, float p, cudaStream_t s) {
   if (Nq > 128 || Nk > 128 || !aligned16(q, ldq) || !aligned16(k, ldk) || !aligned16(v, ldv) || !aligned16(o, ldo) ||
       !aligned16(dout, lddo) || !aligned16(dq, lddq) || !aligned16(dk, lddk) || !aligned16(dv, lddv))
     return MMNAS_ERR_UNSUPPORTED;
-  if (bias_il && (Nk & 3)) return MMNAS_ERR_UNSUPPORTED;
   CUtensorMap tq, tk, tv, tdo;
   int rc;
   if ((rc = encode_2d(&tq, q, heads * 64, (long)B * Nq, ldq, 64, 128))) return rc;
@@ -533,7 +522,6 @@ int mmnas_attn_bwd_tc(int B, int heads, int Nq, int Nk, const void* q, long ldq,
   a.dout = (const __nv_bfloat16*)dout; a.lddo = lddo;
   a.dq = (__nv_bfloat16*)dq; a.dk = (__nv_bfloat16*)dk; a.dv = (__nv_bfloat16*)dv;
   a.lddq = lddq; a.lddk = lddk; a.lddv = lddv; a.dbias = dbias;
-  a.bias_il = bias_il;
   static bool attr_done = false;
   if (!attr_done) {
     MMNAS_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));

@@ -13,34 +13,7 @@
 #include "common.cuh"
 #include "../../include/mmnas_b200.h"
 
-// internal entry points of the tensor-core attention and relation-bias kernels (attention_tc.cu, relbias_mma.cu) with the
-// bias-layout switch that only the block-level calls use
-int mmnas_attn_fwd_tc(int B, int heads, int Nq, int Nk, const void* q, long ldq, const void* k, long ldk, const void* v,
-                      long ldv, const unsigned char* kmask, const float* bias, void* o, long ldo, float scale,
-                      const unsigned long long* rng_state, unsigned long long salt, float p, cudaStream_t s, int bias_il);
-int mmnas_attn_bwd_tc(int B, int heads, int Nq, int Nk, const void* q, long ldq, const void* k, long ldk, const void* v,
-                      long ldv, const unsigned char* kmask, const float* bias, const void* o, long ldo, const void* dout,
-                      long lddo, void* dq, long lddq, void* dk, long lddk, void* dv, long lddv, float* dbias, float scale,
-                      const unsigned long long* rng_state, unsigned long long salt, float p, cudaStream_t s, int bias_il);
-int mmnas_relbias_fwd_mma(int B, int N, int heads, const float* g4, const float* Wy, const float* by, const float* Wr,
-                          const float* br, float* bias, cudaStream_t s, int il);
-int mmnas_relbias_bwd_mma(int B, int N, int heads, const float* g4, const float* Wy, const float* by, const float* Wr,
-                          const float* br, const float* dbias, float* dWy, float* dby, float* dWr, float* dbr,
-                          cudaStream_t s, int il);
-
 namespace {
-
-// RSA logit bias between the geometry kernel and the attention kernel: in the bf16 arm with the geometry input both sides
-// are this library's tensor-core kernels, and the [B, heads, N, N] fp32 planes are exchanged ROW-INTERLEAVED ((i, j) at
-// ((j / 4) N + i) 4 + j % 4): the attention kernel's thread-per-row 16-byte reads and dbias writes become contiguous
-// 512-byte runs per warp instead of 32 separate lines (14 us of a 34 us forward at B = 64, N = 100).  A pure function of
-// the descriptor, so forward and backward agree.  MMNAS_BIAS_IL=0 keeps the natural layout (A/B runs).
-bool bias_interleaved(const mmnas_att_block* d, int heads) {
-  static const bool enabled = !(getenv("MMNAS_BIAS_IL") && atoi(getenv("MMNAS_BIAS_IL")) == 0);
-  return enabled && d->precision == 1 && d->R && d->g4 && d->Nq == d->Nk && (d->Nq & 3) == 0 && d->Nq <= 128 &&
-         heads >= 2 && heads <= 8 && (heads & 1) == 0 && ((uintptr_t)d->g4 % 16) == 0 && ((uintptr_t)d->Wy % 16) == 0;
-}
-
 
 #define RC(call)                 \
   do {                           \
@@ -292,21 +265,15 @@ int att_fwd(const mmnas_att_block* d, bool rel) {
   }
   // --- RSA logit bias from the geometry path
   float* bias = nullptr;
-  const bool il = bias_interleaved(d, heads);
   if (d->R) {
     bias = (float*)(ws + L.bias);
-    if (il) RC(mmnas_relbias_fwd_mma(B, Nq, heads, d->g4, d->Wy, d->by, d->Wr, d->br, bias, (cudaStream_t)s, 1));
-    else if (d->g4) RC(mmnas_relbias_fwd(bf ? 1 : 0, B, Nq, heads, d->R, nullptr, d->g4, d->Wy, d->by, d->Wr, d->br, bias, s));
+    if (d->g4) RC(mmnas_relbias_fwd(bf ? 1 : 0, B, Nq, heads, d->R, nullptr, d->g4, d->Wy, d->by, d->Wr, d->br, bias, s));
     else RC(mmnas_relbias_fwd(0, B, Nq, heads, d->R, d->rel, nullptr, nullptr, nullptr, d->Wr, d->br, bias, s));
   }
   // --- attention core, merged-head output
   void* atted = ws + L.atted;
-  if (il)
-    RC(mmnas_attn_fwd_tc(B, heads, Nq, Nk, P.q, P.ldq, P.k, P.ldk, P.v, P.ldv, d->kmask, bias, atted, I, 0.125f,
-                         d->p_att > 0.f ? rng : nullptr, d->salt_att, d->p_att, (cudaStream_t)s, 1));
-  else
-    RC(mmnas_attn_fwd(bf ? 1 : 0, B, heads, Nq, Nk, HEAD, P.q, P.ldq, P.k, P.ldk, P.v, P.ldv, d->kmask, bias, atted, I, 0.125f,
-                      d->p_att > 0.f ? rng : nullptr, d->salt_att, d->p_att, s));
+  RC(mmnas_attn_fwd(bf ? 1 : 0, B, heads, Nq, Nk, HEAD, P.q, P.ldq, P.k, P.ldk, P.v, P.ldv, d->kmask, bias, atted, I, 0.125f,
+                    d->p_att > 0.f ? rng : nullptr, d->salt_att, d->p_att, s));
   // --- merge projection, residual, LayerNorm (z = x + dropout(branch) overwrites the branch buffer)
   float* z = (float*)(ws + L.z);
   const unsigned long long* rng_out = d->p_out > 0.f ? rng : nullptr;
@@ -376,23 +343,15 @@ int att_bwd(const mmnas_att_block* d, bool rel) {
   char* dkvb = bw + L.dkvb;
   const AttPtrs G = att_views(d, dqkv, dkvb);
   float* dbias = d->R ? (float*)(bw + L.dbias) : nullptr;
-  const bool il = bias_interleaved(d, heads);
-  if (il)
-    RC(mmnas_attn_bwd_tc(B, heads, Nq, Nk, P.q, P.ldq, P.k, P.ldk, P.v, P.ldv, d->kmask, bias, atted, I, datt, I, G.q, G.ldq,
-                         G.k, G.ldk, G.v, G.ldv, dbias, 0.125f, d->p_att > 0.f ? rng : nullptr, d->salt_att, d->p_att, (cudaStream_t)s, 1));
-  else
-    RC(mmnas_attn_bwd(bf ? 1 : 0, B, heads, Nq, Nk, HEAD, P.q, P.ldq, P.k, P.ldk, P.v, P.ldv, d->kmask, bias, atted, I, datt, I,
-                      G.q, G.ldq, G.k, G.ldk, G.v, G.ldv, dbias, 0.125f, d->p_att > 0.f ? rng : nullptr, d->salt_att, d->p_att, s));
+  RC(mmnas_attn_bwd(bf ? 1 : 0, B, heads, Nq, Nk, HEAD, P.q, P.ldq, P.k, P.ldk, P.v, P.ldv, d->kmask, bias, atted, I, datt, I,
+                    G.q, G.ldq, G.k, G.ldk, G.v, G.ldv, dbias, 0.125f, d->p_att > 0.f ? rng : nullptr, d->salt_att, d->p_att, s));
   // --- geometry-bias backward (the kernels accumulate with atomics)
   if (d->R) {
     if (!acc) { RC(zero_f32(d->dWr, (size_t)heads * d->R, s)); RC(zero_f32(d->dbr, heads, s)); }
     if (d->g4) {
       if (!d->accumulate_geometry) { RC(zero_f32(d->dWy, (size_t)d->R * 4, s)); RC(zero_f32(d->dby, d->R, s)); }
-      if (il)
-        RC(mmnas_relbias_bwd_mma(B, Nq, heads, d->g4, d->Wy, d->by, d->Wr, d->br, dbias, d->dWy, d->dby, d->dWr, d->dbr, (cudaStream_t)s, 1));
-      else
-        RC(mmnas_relbias_bwd(bf ? 1 : 0, B, Nq, heads, d->R, nullptr, d->g4, d->Wy, d->by, d->Wr, d->br, dbias, nullptr, d->dWy,
-                             d->dby, d->dWr, d->dbr, s));
+      RC(mmnas_relbias_bwd(bf ? 1 : 0, B, Nq, heads, d->R, nullptr, d->g4, d->Wy, d->by, d->Wr, d->br, dbias, nullptr, d->dWy,
+                           d->dby, d->dWr, d->dbr, s));
     } else {
       RC(mmnas_relbias_bwd(0, B, Nq, heads, d->R, d->rel, nullptr, nullptr, nullptr, d->Wr, d->br, dbias, d->drel, nullptr,
                            nullptr, d->dWr, d->dbr, s));

@@ -370,10 +370,10 @@ int launch_bwd(const RelArgs& a, cudaStream_t s) {
 }  // namespace
 
 int mmnas_relbias_fwd_mma(int B, int N, int heads, const float* g4, const float* Wy, const float* by, const float* Wr,
-                          const float* br, float* bias, cudaStream_t s, int il);
+                          const float* br, float* bias, cudaStream_t s);
 int mmnas_relbias_bwd_mma(int B, int N, int heads, const float* g4, const float* Wy, const float* by, const float* Wr,
                           const float* br, const float* dbias, float* dWy, float* dby, float* dWr, float* dbr,
-                          cudaStream_t s, int il);
+                          cudaStream_t s);
 
 extern "C" int mmnas_relbias_fwd(int mode, int B, int N, int heads, int Rin, const float* rel, const float* g4,
                                  const float* Wy, const float* by, const float* Wr, const float* br, float* bias,
@@ -385,7 +385,7 @@ extern "C" int mmnas_relbias_fwd(int mode, int B, int N, int heads, int Rin, con
   MMNAS_CHECK_ARG(bias, "relbias_fwd: null output");
   cudaStream_t s = (cudaStream_t)stream;
   if (mode == 1 && g4) {
-    rc = mmnas_relbias_fwd_mma(B, N, heads, g4, Wy, by, Wr, br, bias, s, 0);
+    rc = mmnas_relbias_fwd_mma(B, N, heads, g4, Wy, by, Wr, br, bias, s);
     if (rc != MMNAS_ERR_UNSUPPORTED) return rc;
   }
   RelArgs a = {};
@@ -406,7 +406,7 @@ extern "C" int mmnas_relbias_bwd(int mode, int B, int N, int heads, int Rin, con
   MMNAS_CHECK_ARG(!g4 || (dWy && dby), "relbias_bwd: geometry mode needs dWy/dby outputs");
   cudaStream_t s = (cudaStream_t)stream;
   if (mode == 1 && g4) {
-    rc = mmnas_relbias_bwd_mma(B, N, heads, g4, Wy, by, Wr, br, dbias, dWy, dby, dWr, dbr, s, 0);
+    rc = mmnas_relbias_bwd_mma(B, N, heads, g4, Wy, by, Wr, br, dbias, dWy, dby, dWr, dbr, s);
     if (rc != MMNAS_ERR_UNSUPPORTED) return rc;
   }
   RelArgs a = {};

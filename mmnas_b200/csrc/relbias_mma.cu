@@ -40,9 +40,6 @@ struct MmaArgs {
   float* bias;
   const float* dbias;
   float *dWy, *dby, *dWr, *dbr;
-  int il;                    // bias / dbias planes row-interleaved: (i, j) at ((j / 4) N + i) 4 + j % 4 (attention_tc.cu)
-  unsigned n;                // N (regions per image)
-  float inv_n;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -140,15 +137,7 @@ __global__ void __launch_bounds__(THREADS, 2) relbias_mma_kernel(MmaArgs a) {
         live[mt][rh] = base + d < a.pairs && myheads;
         unsigned b = bb, ij = ij_base + d;
         while (ij >= a.nn) { ij -= a.nn; ++b; }
-        unsigned within = ij;
-        if (a.il) {
-          unsigned i = (unsigned)(__uint2float_rz(ij) * a.inv_n);
-          if (i * a.n > ij) --i;
-          if ((i + 1) * a.n <= ij) ++i;
-          const unsigned j = ij - i * a.n;
-          within = ((j >> 2) * a.n + i) * 4 + (j & 3);
-        }
-        off[mt][rh] = ((size_t)b * a.heads + 2 * q) * a.nn + within;
+        off[mt][rh] = ((size_t)b * a.heads + 2 * q) * a.nn + ij;
         gv[mt][rh] = gnext[mt][rh];
         if (BWD) {        // issued early: latency hides behind the first layer
           db[mt][rh][0] = live[mt][rh] ? __ldg(a.dbias + off[mt][rh]) : 0.f;
@@ -288,11 +277,9 @@ int grid_for(unsigned pairs, unsigned pairs_per_iter, unsigned ctas_per_sm) {
 
 // Returns MMNAS_ERR_UNSUPPORTED when the configuration is outside this kernel (caller then uses relbias.cu).
 int mmnas_relbias_fwd_mma(int B, int N, int heads, const float* g4, const float* Wy, const float* by, const float* Wr,
-                          const float* br, float* bias, cudaStream_t s, int il) {
+                          const float* br, float* bias, cudaStream_t s) {
   if (heads > HEADS || heads < 2 || (heads & 1) || !g4 || ((uintptr_t)g4 % 16) != 0 || ((uintptr_t)Wy % 16) != 0) return MMNAS_ERR_UNSUPPORTED;
-  if (il && (N & 3)) return MMNAS_ERR_UNSUPPORTED;
   MmaArgs a = {};
-  a.il = il; a.n = (unsigned)N; a.inv_n = 1.0f / (float)N;
   a.nn = (unsigned)N * N; a.pairs = (unsigned)B * a.nn;
   a.heads = heads;
   a.g4 = g4; a.Wy = Wy; a.by = by; a.Wr = Wr; a.br = br; a.bias = bias;
@@ -302,11 +289,9 @@ int mmnas_relbias_fwd_mma(int B, int N, int heads, const float* g4, const float*
 
 int mmnas_relbias_bwd_mma(int B, int N, int heads, const float* g4, const float* Wy, const float* by, const float* Wr,
                           const float* br, const float* dbias, float* dWy, float* dby, float* dWr, float* dbr,
-                          cudaStream_t s, int il) {
+                          cudaStream_t s) {
   if (heads > HEADS || heads < 2 || (heads & 1) || !g4 || ((uintptr_t)g4 % 16) != 0 || ((uintptr_t)Wy % 16) != 0) return MMNAS_ERR_UNSUPPORTED;
-  if (il && (N & 3)) return MMNAS_ERR_UNSUPPORTED;
   MmaArgs a = {};
-  a.il = il; a.n = (unsigned)N; a.inv_n = 1.0f / (float)N;
   a.nn = (unsigned)N * N; a.pairs = (unsigned)B * a.nn;
   a.heads = heads;
   a.g4 = g4; a.Wy = Wy; a.by = by; a.Wr = Wr; a.br = br; a.dbias = dbias;
