@@ -99,3 +99,20 @@ def test_synthetic_batches_have_the_baseline_shapes():
     assert f.shape == (9, 36, 2048) and q.shape == (9, 50)
     assert torch.equal(f[0:3], f[3:6]) and torch.equal(q[0:3], q[6:9])   # negc keeps the images, negi the captions
     assert not torch.equal(q[0:3], q[3:6]) and not torch.equal(f[0:3], f[6:9])
+
+
+def test_sink_prepare_is_refused_inside_a_side_stream_fork():
+    """functional._Fork moves only the library's launches to the side stream; a torch fill issued inside the block would
+    run on the main stream and race them (the LSTM weight-gradient bug of round 2).  _Sink.prepare() must refuse."""
+    import pytest
+    from mmnas_b200 import functional as Fn
+    w = torch.nn.Parameter(torch.zeros(4, 3))
+    sink = Fn._Sink((w,), torch.device('cpu'))
+    sink.prepare(zero=True)                       # outside a fork: fine
+    assert sink.buf.shape == (4, 3) and not sink.direct
+    Fn._Fork.depth += 1
+    try:
+        with pytest.raises(RuntimeError, match='inside'):
+            Fn._Sink((w,), torch.device('cpu')).prepare(zero=True)
+    finally:
+        Fn._Fork.depth -= 1
