@@ -391,7 +391,7 @@ def run_b200(args):
     import mmnas_b200
     from mmnas_b200 import _lib, genotypes
     from mmnas_b200.data.synthetic import Cfg, SynthSpec, make_batch, init_dict, compact
-    from mmnas_b200.engine import TrainStep, Prefetcher
+    from mmnas_b200.engine import TrainStep, Prefetcher, ScalarLog
     from mmnas_b200.model.nets import Net_Full
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -455,12 +455,20 @@ def run_b200(args):
         b_in, b_t = pre.next()
         float(step(b_in, b_t))
     barrier()
+    log = ScalarLog(dev)
+    losses = []
     e0.record()
     for _ in range(args.steps):
         b_in, b_t = pre.next()
-        last = float(step(b_in, b_t))             # device->host read of the step's loss
+        log.push(step(b_in, b_t))                 # device->host copy of this step's loss, enqueued behind the step ...
+        if len(log) > 1:
+            losses.append(log.pop())              # ... and read on the host while the next step is already queued
+    while len(log):
+        losses.append(log.pop())
+    last = losses[-1]
     e1.record()
     barrier()
+    assert len(losses) == args.steps and all(v == v for v in losses)
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -468,7 +476,9 @@ def run_b200(args):
     e2e = {'value': BATCH * world / (e2e_ms / 1e3), 'unit': 'samples/s', 'ms_per_step': e2e_ms,
            'h2d_bytes_per_step': pre.bytes_per_batch, 'd2h_bytes_per_step': 4,
            'how': 'pinned host batch (bf16 region features, raw boxes, question tokens, answer scores) -> device on a copy '
-                  'stream one step ahead, TrainStep(...) incl. the box-geometry kernel, float(loss)'}
+                  'stream one step ahead, TrainStep(...) incl. the box-geometry kernel, every step\'s loss copied to pinned '
+                  'host memory behind the step and read by the host one step later (engine.ScalarLog), all inside the '
+                  'timed region'}
 
     # ---- live per-kernel timing (CUDA events around every C-ABI call, eager, same workload) -> roofline
     prof_step = step if not use_graph else TrainStep(net, lr_base=cfg.NET_LR_BASE, epoch_steps=10 ** 6, use_graph=False)

@@ -750,3 +750,35 @@ class Prefetcher:
             t.record_stream(torch.cuda.current_stream(self.device))
         self._issue()
         return batch
+
+
+class ScalarLog:
+    """Per-step scalars (the loss) to the host without stalling the launch queue: push() enqueues a non-blocking
+    device->host copy into pinned memory behind the step that produced the value, pop() returns the oldest pushed value
+    (waiting for its copy only).  Reading step t's loss while step t+1 is already queued keeps the GPU busy; a
+    synchronous float(loss) after every step leaves it idle for the host's launch latency each time."""
+
+    def __init__(self, device, depth=4):
+        self.device = torch.device(device)
+        self.slots = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.events = [torch.cuda.Event() for _ in range(depth)]
+        self.head = self.tail = 0
+
+    def __len__(self):
+        return self.head - self.tail
+
+    def push(self, value):
+        if len(self) == len(self.slots):
+            raise RuntimeError('ScalarLog full: pop() before pushing more')
+        i = self.head % len(self.slots)
+        self.slots[i].copy_(value.detach().reshape(1), non_blocking=True)
+        self.events[i].record(torch.cuda.current_stream(self.device))
+        self.head += 1
+
+    def pop(self):
+        if not len(self):
+            raise RuntimeError('ScalarLog empty')
+        i = self.tail % len(self.slots)
+        self.events[i].synchronize()
+        self.tail += 1
+        return float(self.slots[i][0])

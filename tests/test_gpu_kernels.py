@@ -623,3 +623,21 @@ def test_native_lstm_matches_torch_lstm(B, T, E, H):
     with mmnas_b200.precision('bf16'), torch.no_grad():
         out2 = LSTMFn.apply(e32, *params)
     assert torch.equal(out.detach(), out2)
+
+
+def test_scalar_log_returns_pushed_values_in_order():
+    """engine.ScalarLog: non-blocking device->host reads of per-step scalars, popped in push order."""
+    from mmnas_b200.engine import ScalarLog
+    log = ScalarLog(DEV, depth=3)
+    src = torch.zeros((), device=DEV)
+    got = []
+    for i in range(7):
+        src.fill_(float(i) + 0.5)            # same tensor every step, like a graph's static loss
+        log.push(src)
+        if len(log) > 1:
+            got.append(log.pop())
+    while len(log):
+        got.append(log.pop())
+    assert got == [i + 0.5 for i in range(7)]
+    with pytest.raises(RuntimeError):
+        log.pop()
