@@ -508,7 +508,7 @@ class SearchStep:
         # Segmented replay (see _Segments): everything around the sampled backbone is static, so it replays from four
         # CUDA graphs while the backbone stays a sequence of block-level calls chosen per step.
         self.presample = self.net_params[0].is_cuda and os.environ.get('MMNAS_PRESAMPLE', '1') != '0'
-        self.use_segments = (segments and self.executor is not None
+        self.use_segments = (segments and self.executor is not None and getattr(net, 'rel_mode', 'geometry') == 'geometry'
                              and os.environ.get('MMNAS_SEARCH_SEGMENTS', '1') != '0')
         self._seg = None
 
