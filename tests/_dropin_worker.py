@@ -7,7 +7,12 @@ scripts/install_reference.py) and runs, on cuda:0 in float32:
   1. full_vqa.Net_Full with the genotype read from baseline/_ref/arch/mmnas_vqa.json exactly as train_vqa.py:185 does,
      one train-step body (train_vqa.py:294-299): logits, loss, every parameter gradient;
   2. hygr_vqa.Net_Search, one architecture-step body in MODE 'full' (search_vqa.py:317-331) driven through the
-     reference's own bookkeeping (reset_binary_gates / unused_modules_off / set_arch_param_grad / genotype).
+     reference's own bookkeeping (reset_binary_gates / unused_modules_off / set_arch_param_grad / genotype);
+  3. full_vgd.Net_Full (arch/mmnas_vgd.json, 100 regions x 15 query tokens), the step body of train_vgd.py:317-336
+     (KLD over the masked region scores + 0.5 SmoothL1 over the masked box regressions, LOSS_AVG);
+  4. full_itm.Net_Full (arch/mmnas_itm.json, 36 regions x 50 caption tokens), the step body of train_itm.py:384-392:
+     three forwards (positive, negative captions, negative images) and the reference's own BCE_Loss
+     (mmnas/utils/itm_loss.py, positive term twice).
 With `ours`, mmnas_b200.install_as_mmnas() first replaces mmnas.model.modules, mmnas.model.mixed and
 mmnas.utils.ops_adapter, so the reference's nets run on this library's CUDA operators; with `ref` nothing is replaced."""
 import json
@@ -88,7 +93,58 @@ def main():
                      'grads': {n: p.grad.detach().cpu() for n, p in net.named_net_parameters() if p.grad is not None}}
     if impl == 'ours':
         from mmnas_b200 import _lib
-        res['launches'] = _lib.launches()
+        res['launches'] = _lib.launches()               # kernels of the library launched by 1. and 2.
+    del net, pred, loss
+
+    # ---- 3. VGD train-time net (RSA-heavy decoder, grounding head) through the step body of train_vgd.py:317-336
+    from mmnas.model import full_vgd, full_itm
+    from mmnas.utils.itm_loss import BCE_Loss
+    from mmnas_b200.data.synthetic import spec_for
+    geno = json.load(open(os.path.join(REF, 'arch', 'mmnas_vgd.json')))['epoch0']
+    spec = spec_for('vgd', batch=4, vocab=1000)
+    cfg = Cfg(genotype=geno, DROPOUT_R=0.0, SCORES_LOSS='kld', LOSS_AVG=True, LOSS_LAMBDA=0.5, REDUCTION='sum')
+    inputs, target = make_batch(spec, 888)
+    torch.manual_seed(888)
+    net = full_vgd.Net_Full(cfg, init_dict(spec))
+    with torch.no_grad():
+        condition_rsa_(dict(net.named_parameters()))
+    net = net.to(dev).train()
+    scores, scores_mask, tbox, bbox_mask = (t.to(dev) for t in target)
+    pred_scores, pred_reg = net(tuple(t.to(dev) for t in inputs))
+    loss_scores = torch.nn.KLDivLoss(reduction=cfg.REDUCTION)(pred_scores * scores_mask, scores * scores_mask)
+    loss_reg = torch.nn.SmoothL1Loss(reduction=cfg.REDUCTION)(pred_reg * bbox_mask, tbox * bbox_mask)
+    loss = loss_scores / torch.sum(scores_mask.data) + cfg.LOSS_LAMBDA * (loss_reg / torch.sum(bbox_mask.data))
+    loss.backward()
+    res['vgd'] = {'pred': pred_scores.detach().cpu(), 'pred_reg': pred_reg.detach().cpu(), 'loss': loss.detach().cpu(),
+                  'grads': {n: p.grad.detach().cpu() for n, p in net.named_parameters() if p.grad is not None},
+                  'keys': {k: tuple(v.shape) for k, v in net.state_dict().items()}}
+    del net, pred_scores, pred_reg, loss
+
+    # ---- 4. ITM train-time net, three forwards + BCE_Loss (train_itm.py:384-392)
+    geno = json.load(open(os.path.join(REF, 'arch', 'mmnas_itm.json')))['epoch0']
+    spec = spec_for('itm', batch=2, vocab=1000)
+    cfg = Cfg(genotype=geno, DROPOUT_R=0.0, REDUCTION='sum')
+    # rows [0,B) positive | [B,2B) negative captions | [2B,3B) negative images.  Batch seed 892: with 888 / 889 one FFN /
+    # AttFlat hidden unit has a pre-activation within float32 rounding of zero, so even the reference's own float32 and
+    # float64 evaluations disagree on that ReLU branch (2.7e-3 / 1.1e-2 on mlp.fc.linear.weight); with 892 they agree
+    # to 2e-6 on every tensor, so the comparison measures the operators and not the coin flip
+    inputs, _ = make_batch(spec, 892)
+    torch.manual_seed(888)
+    net = full_itm.Net_Full(cfg, init_dict(spec))
+    with torch.no_grad():
+        condition_rsa_(dict(net.named_parameters()))
+    net = net.to(dev).train()
+    B = spec.batch
+    parts = [tuple(t[i * B:(i + 1) * B].to(dev) for t in inputs) for i in range(3)]
+    scores_pos, scores_negc, scores_negi = net(parts[0]), net(parts[1]), net(parts[2])
+    loss = BCE_Loss(cfg)(scores_pos, scores_negc, scores_negi)
+    loss.backward()
+    res['itm'] = {'pred': torch.cat((scores_pos, scores_negc, scores_negi)).detach().cpu(), 'loss': loss.detach().cpu(),
+                  'grads': {n: p.grad.detach().cpu() for n, p in net.named_parameters() if p.grad is not None},
+                  'keys': {k: tuple(v.shape) for k, v in net.state_dict().items()}}
+    if impl == 'ours':
+        from mmnas_b200 import _lib
+        res['launches_total'] = _lib.launches()
     torch.save(res, out_path)
 
 

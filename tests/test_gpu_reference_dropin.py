@@ -1,9 +1,11 @@
 """The drop-in claim on hardware: the reference's OWN callers — mmnas/model/full_vqa.py Net_Full (genotype from the
-reference's arch/mmnas_vqa.json) and mmnas/model/hygr_vqa.py Net_Search with its supernet bookkeeping — run on this
-library's CUDA operators through mmnas_b200.install_as_mmnas(), against the untouched reference (its PyTorch ops) on
-the same GPU, float32: logits, loss and gradients within the fp32 tolerance of north_star, same sampled path under the
-same seed, same genotype.  The reference files are the byte-identical copy under baseline/_ref/ (git-ignored,
-populated by scripts/install_reference.py / __graft_entry__.build(); the manifest's sha256 sums are re-checked)."""
+reference's arch/mmnas_vqa.json), mmnas/model/hygr_vqa.py Net_Search with its supernet bookkeeping, and the VGD / ITM
+nets full_vgd.py / full_itm.py (arch/mmnas_vgd.json, arch/mmnas_itm.json) through the step bodies of train_vgd.py /
+train_itm.py — run on this library's CUDA operators through mmnas_b200.install_as_mmnas(), against the untouched
+reference (its PyTorch ops) on the same GPU, float32: logits, loss and gradients within the fp32 tolerance of
+north_star, same sampled path under the same seed, same genotype.  The reference files are the byte-identical copy
+under baseline/_ref/ (git-ignored, populated by scripts/install_reference.py / __graft_entry__.build(); the manifest's
+sha256 sums are re-checked)."""
 import os
 import subprocess
 import sys
@@ -73,3 +75,30 @@ def test_reference_net_search_arch_step_runs_on_the_cuda_operators(runs):
     for n_, g in ref['grads'].items():
         pr.add(n_, ours['grads'][n_], g, _tol(n_), floor)
     pr.check()
+
+
+def _train_net_parity(label, ref, ours, extra=()):
+    assert ours['keys'] == ref['keys']                         # checkpoint-compatible state dict
+    pr = Parity(label)
+    pr.add('pred', ours['pred'], ref['pred'], 1e-5)
+    for k in extra:
+        pr.add(k, ours[k], ref[k], 1e-5)
+    pr.add('loss', ours['loss'], ref['loss'], 1e-5)
+    floor = 1e-2 * max(float(g.abs().max()) for g in ref['grads'].values())
+    assert set(ours['grads']) == set(ref['grads'])
+    for n_, g in ref['grads'].items():
+        pr.add(n_, ours['grads'][n_], g, _tol(n_), floor)
+    pr.check()
+
+
+def test_reference_vgd_net_runs_on_the_cuda_operators(runs):
+    """BASELINE configs[3]'s caller: full_vgd.Net_Full from arch/mmnas_vgd.json (6 RSA blocks, grounding head with
+    region scores + box regression), loss of train_vgd.py:320-334."""
+    _train_net_parity('dropin/full_vgd.Net_Full/fp32', runs['ref']['vgd'], runs['ours']['vgd'], extra=('pred_reg',))
+
+
+def test_reference_itm_net_runs_on_the_cuda_operators(runs):
+    """BASELINE configs[4]'s caller: full_itm.Net_Full from arch/mmnas_itm.json, three forwards of one net before one
+    backward (train_itm.py:387-391) and the reference's BCE_Loss — every operator instance holds three live
+    workspaces at once."""
+    _train_net_parity('dropin/full_itm.Net_Full/fp32', runs['ref']['itm'], runs['ours']['itm'])
