@@ -1,6 +1,6 @@
 """Worker of tests/test_gpu_reference_dropin.py (run as a subprocess, one per implementation).
 
-    python tests/_dropin_worker.py {ours|ref} OUT.pt
+    python tests/_dropin_worker.py {ours|ours_bf16|ref} OUT.pt
 
 Imports the UNMODIFIED reference callers from baseline/_ref (mmnas/model/full_vqa.py, hygr_vqa.py — populated by
 scripts/install_reference.py) and runs, on cuda:0 in float32:
@@ -14,7 +14,8 @@ scripts/install_reference.py) and runs, on cuda:0 in float32:
      three forwards (positive, negative captions, negative images) and the reference's own BCE_Loss
      (mmnas/utils/itm_loss.py, positive term twice).
 With `ours`, mmnas_b200.install_as_mmnas() first replaces mmnas.model.modules, mmnas.model.mixed and
-mmnas.utils.ops_adapter, so the reference's nets run on this library's CUDA operators; with `ref` nothing is replaced."""
+mmnas.utils.ops_adapter, so the reference's nets run on this library's CUDA operators; with `ref` nothing is replaced.
+`ours_bf16` is `ours` in the bf16 arm (tcgen05 kernels; train-time nets 1, 3, 4 only)."""
 import json
 import os
 import sys
@@ -32,10 +33,13 @@ def main():
     sys.path.insert(1, REF)
     torch.backends.cudnn.allow_tf32 = False           # the callers' cuDNN LSTM in true fp32 for both implementations
     torch.backends.cuda.matmul.allow_tf32 = False
+    bf16 = impl == 'ours_bf16'
+    if bf16:
+        impl = 'ours'
     if impl == 'ours':
         import mmnas_b200
         mmnas_b200.install_as_mmnas()
-        mmnas_b200.set_precision('fp32')
+        mmnas_b200.set_precision('bf16' if bf16 else 'fp32')
     from mmnas.model.full_vqa import Net_Full
     from mmnas.model.hygr_vqa import Net_Search
     from mmnas.model.mixed import MixedOp
@@ -64,6 +68,13 @@ def main():
                    'keys': {k: tuple(v.shape) for k, v in net.state_dict().items()}}
     del net, pred, loss
 
+    if not bf16:
+        search_arch_step(res, Net_Search, MixedOp, Cfg, init_dict, condition_rsa_, spec, inputs, target, dev, impl)
+    train_nets(res, Cfg, make_batch, init_dict, condition_rsa_, dev, impl)
+    torch.save(res, out_path)
+
+
+def search_arch_step(res, Net_Search, MixedOp, Cfg, init_dict, condition_rsa_, spec, inputs, target, dev, impl):
     # ---- 2. supernet, MODE 'full' architecture step through the reference's own Net_Search methods
     cfg = Cfg(mode='search', DROPOUT_R=0.0)
     torch.manual_seed(888)
@@ -94,8 +105,9 @@ def main():
     if impl == 'ours':
         from mmnas_b200 import _lib
         res['launches'] = _lib.launches()               # kernels of the library launched by 1. and 2.
-    del net, pred, loss
 
+
+def train_nets(res, Cfg, make_batch, init_dict, condition_rsa_, dev, impl):
     # ---- 3. VGD train-time net (RSA-heavy decoder, grounding head) through the step body of train_vgd.py:317-336
     from mmnas.model import full_vgd, full_itm
     from mmnas.utils.itm_loss import BCE_Loss
@@ -145,7 +157,6 @@ def main():
     if impl == 'ours':
         from mmnas_b200 import _lib
         res['launches_total'] = _lib.launches()
-    torch.save(res, out_path)
 
 
 if __name__ == '__main__':

@@ -29,7 +29,7 @@ def runs():
         pytest.fail('baseline/_ref is missing or modified: run scripts/install_reference.py in the authoring container')
     out = {}
     with tempfile.TemporaryDirectory() as tmp:
-        for impl in ('ref', 'ours'):
+        for impl in ('ref', 'ours', 'ours_bf16'):
             path = os.path.join(tmp, impl + '.pt')
             r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', '_dropin_worker.py'), impl, path],
                                capture_output=True, text=True, cwd=ROOT)
@@ -102,3 +102,23 @@ def test_reference_itm_net_runs_on_the_cuda_operators(runs):
     backward (train_itm.py:387-391) and the reference's BCE_Loss — every operator instance holds three live
     workspaces at once."""
     _train_net_parity('dropin/full_itm.Net_Full/fp32', runs['ref']['itm'], runs['ours']['itm'])
+
+
+@pytest.mark.parametrize('task', ['full', 'vgd', 'itm'])
+def test_reference_train_nets_run_on_the_bf16_arm(runs, task):
+    """The same reference callers with mmnas_b200.set_precision('bf16') (the tcgen05 kernels: what a user switching to
+    this library actually trains with) against the untouched float32 reference: logits / scores and loss within
+    north_star's 2e-2, gradients within the bf16 gate of tests/test_gpu_nets.py (5e-2 Frobenius-relative)."""
+    ref, ours = runs['ref'][task], runs['ours_bf16'][task]
+    assert runs['ours_bf16']['modules'] == 'mmnas_b200.model.modules'
+    assert ours['keys'] == ref['keys']
+    pr = Parity('dropin/%s.Net_Full/bf16' % {'full': 'full_vqa', 'vgd': 'full_vgd', 'itm': 'full_itm'}[task])
+    pr.add('pred', ours['pred'], ref['pred'], 2e-2)
+    if task == 'vgd':
+        pr.add('pred_reg', ours['pred_reg'], ref['pred_reg'], 2e-2)
+    pr.add('loss', ours['loss'], ref['loss'], 2e-2)
+    floor = 1e-2 * max(float(g.abs().max()) for g in ref['grads'].values())
+    assert set(ours['grads']) == set(ref['grads'])
+    for n_, g in ref['grads'].items():
+        pr.add(n_, ours['grads'][n_], g, 5e-2, floor, metric='fro')
+    pr.check()
