@@ -12,7 +12,9 @@ scripts/install_reference.py) and runs, on cuda:0 in float32:
      (KLD over the masked region scores + 0.5 SmoothL1 over the masked box regressions, LOSS_AVG);
   4. full_itm.Net_Full (arch/mmnas_itm.json, 36 regions x 50 caption tokens), the step body of train_itm.py:384-392:
      three forwards (positive, negative captions, negative images) and the reference's own BCE_Loss
-     (mmnas/utils/itm_loss.py, positive term twice).
+     (mmnas/utils/itm_loss.py, positive term twice);
+  5. hygr_vgd.Net_Search and hygr_itm.Net_Search, one weight-step body each on the path sampled under seed 888
+     (search_vgd.py / search_itm.py: reset_binary_gates, unused_modules_off, forward, loss, backward).
 With `ours`, mmnas_b200.install_as_mmnas() first replaces mmnas.model.modules, mmnas.model.mixed and
 mmnas.utils.ops_adapter, so the reference's nets run on this library's CUDA operators; with `ref` nothing is replaced.
 `ours_bf16` is `ours` in the bf16 arm (tcgen05 kernels; train-time nets 1, 3, 4 only)."""
@@ -71,6 +73,8 @@ def main():
     if not bf16:
         search_arch_step(res, Net_Search, MixedOp, Cfg, init_dict, condition_rsa_, spec, inputs, target, dev, impl)
     train_nets(res, Cfg, make_batch, init_dict, condition_rsa_, dev, impl)
+    if not bf16:
+        search_weight_steps(res, Cfg, make_batch, init_dict, condition_rsa_, dev)
     torch.save(res, out_path)
 
 
@@ -157,6 +161,55 @@ def train_nets(res, Cfg, make_batch, init_dict, condition_rsa_, dev, impl):
     if impl == 'ours':
         from mmnas_b200 import _lib
         res['launches_total'] = _lib.launches()
+
+
+def vgd_step_loss(cfg, pred, target):
+    """train_vgd.py:319-334 with the shipped settings (SCORES_LOSS 'kld', LOSS_AVG, LOSS_LAMBDA 0.5, REDUCTION 'sum')."""
+    pred_scores, pred_reg = pred
+    scores, scores_mask, tbox, bbox_mask = target
+    loss_scores = torch.nn.KLDivLoss(reduction=cfg.REDUCTION)(pred_scores * scores_mask, scores * scores_mask)
+    loss_reg = torch.nn.SmoothL1Loss(reduction=cfg.REDUCTION)(pred_reg * bbox_mask, tbox * bbox_mask)
+    return loss_scores / torch.sum(scores_mask.data) + cfg.LOSS_LAMBDA * (loss_reg / torch.sum(bbox_mask.data))
+
+
+def search_weight_steps(res, Cfg, make_batch, init_dict, condition_rsa_, dev, dtype=torch.float32, seeds=(888, 892)):
+    # ---- 5. the VGD / ITM supernets (H = 256, 4 heads), weight step on the path sampled under seed 888
+    from mmnas.model import hygr_vgd, hygr_itm
+    from mmnas.model.mixed import MixedOp
+    from mmnas.utils.itm_loss import BCE_Loss
+    from mmnas_b200.data.synthetic import spec_for
+    cast = lambda t: t.to(dev, dtype) if t.is_floating_point() else t.to(dev)        # noqa: E731
+    for task, mod, seed in (('vgd', hygr_vgd, seeds[0]), ('itm', hygr_itm, seeds[1])):
+        spec = spec_for(task, batch=4 if task == 'vgd' else 2, vocab=1000)
+        cfg = Cfg(mode='search', DROPOUT_R=0.0, SCORES_LOSS='kld', LOSS_AVG=True, LOSS_LAMBDA=0.5, REDUCTION='sum')
+        inputs, target = make_batch(spec, seed)
+        torch.manual_seed(888)
+        net = mod.Net_Search(cfg, init_dict(spec))
+        with torch.no_grad():
+            condition_rsa_(dict(net.named_parameters()))
+        net = net.to(dev, dtype).train()
+        MixedOp.MODE = None
+        torch.manual_seed(888)
+        net.reset_binary_gates()
+        net.unused_modules_off()
+        picks = [m.active_index[0] for m in net.redundant_modules]
+        if task == 'vgd':
+            pred = net(tuple(cast(t) for t in inputs))
+            loss = vgd_step_loss(cfg, pred, tuple(cast(t) for t in target))
+            pred = torch.cat((pred[0].reshape(-1), pred[1].reshape(-1)))
+        else:
+            B = spec.batch
+            parts = [tuple(cast(t[i * B:(i + 1) * B]) for t in inputs) for i in range(3)]
+            scores = [net(p) for p in parts]
+            loss = BCE_Loss(cfg)(*scores)
+            pred = torch.cat(scores)
+        net.zero_grad()
+        loss.backward()
+        net.unused_modules_back()
+        res['search_' + task] = {'picks': picks, 'pred': pred.detach().cpu(), 'loss': loss.detach().cpu(),
+                                 'grads': {n: p.grad.detach().cpu() for n, p in net.named_net_parameters()
+                                           if p.grad is not None}}
+        del net, pred, loss
 
 
 if __name__ == '__main__':

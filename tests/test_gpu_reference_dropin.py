@@ -104,6 +104,23 @@ def test_reference_itm_net_runs_on_the_cuda_operators(runs):
     _train_net_parity('dropin/full_itm.Net_Full/fp32', runs['ref']['itm'], runs['ours']['itm'])
 
 
+@pytest.mark.parametrize('task', ['vgd', 'itm'])
+def test_reference_search_nets_weight_step_runs_on_the_cuda_operators(runs, task):
+    """hygr_vgd.Net_Search / hygr_itm.Net_Search (the supernets of search_vgd.py / search_itm.py): the reference's own
+    bookkeeping samples a path under seed 888 through OUR MixedOp, switches the unused candidates off, and one weight-step
+    body runs on the CUDA operators — same path, same scores / loss, same gradients on every sampled candidate."""
+    ref, ours = runs['ref']['search_' + task], runs['ours']['search_' + task]
+    assert ours['picks'] == ref['picks']
+    pr = Parity('dropin/hygr_%s.Net_Search/weight_step/fp32' % task)
+    pr.add('pred', ours['pred'], ref['pred'], 1e-5)
+    pr.add('loss', ours['loss'], ref['loss'], 1e-5)
+    floor = 1e-2 * max(float(g.abs().max()) for g in ref['grads'].values())
+    assert set(ours['grads']) == set(ref['grads'])
+    for n_, g in ref['grads'].items():
+        pr.add(n_, ours['grads'][n_], g, _tol(n_), floor)
+    pr.check()
+
+
 @pytest.mark.parametrize('task', ['full', 'vgd', 'itm'])
 def test_reference_train_nets_run_on_the_bf16_arm(runs, task):
     """The same reference callers with mmnas_b200.set_precision('bf16') (the tcgen05 kernels: what a user switching to
