@@ -127,37 +127,56 @@ def test_registry_and_mixed_op_interface():
     assert m.active_index == [m.chosen_index[0]]
 
 
-@pytest.mark.skipif(not os.path.isdir('/root/reference/mmnas'), reason='reference not mounted')
-def test_drop_in_under_the_reference_nets():
-    """install_as_mmnas(): the reference's own full_vqa.Net_Full builds on the CUDA-backed operators and its
-    state-dict keys / shapes equal those of the untouched reference."""
+REFERENCE_CALLERS = [('full_vqa', 'Net_Full'), ('full_vgd', 'Net_Full'), ('full_itm', 'Net_Full'),
+                     ('hygr_vqa', 'Net_Search'), ('hygr_vgd', 'Net_Search'), ('hygr_itm', 'Net_Search')]
+
+
+@pytest.fixture(scope='module')
+def reference_callers_built():
+    """Builds the reference's six callers twice in subprocesses: untouched ('ref') and after install_as_mmnas() ('ours')."""
+    import json
     import subprocess
     code = r'''
-import sys, json, numpy as np, torch
+import sys, json, importlib, numpy as np, torch
 sys.path.insert(0, %r)
 mode = sys.argv[1]
 sys.path.insert(1, "/root/reference")
 if mode == "ours":
     import mmnas_b200; mmnas_b200.install_as_mmnas()
-from mmnas.model.full_vqa import Net_Full
 import mmnas.model.modules as M
 class C: pass
 c = C()
 c.__dict__.update(HSIZE=128, DROPOUT_R=0.1, REL_SIZE=64, OPS_NORM=True, OPS_RESIDUAL=True, LAYERS=1, BBOX_FEATURE=False,
     FRCNFEAT_SIZE=32, BBOXFEAT_EMB_SIZE=32, WORD_EMBED_SIZE=16, ATTFLAT_GLIMPSES=1, ATTFLAT_OUT_SIZE=256, ATTFLAT_MLP_SIZE=48,
+    SCORES_LOSS="kld", ALPHA_INIT_TYPE="normal", NODES={"enc": 2, "dec": 3},
     GENOTYPE={"enc": [["self_att_64"], ["feed_forward"]], "dec": [["guided_att_64"], ["rel_self_att_64"], ["feed_forward"]]})
-torch.manual_seed(888)
-net = Net_Full(c, {"token_size": 20, "ans_size": 7, "pretrained_emb": np.zeros((20, 16), np.float32)})
-sd = net.state_dict()
-print(json.dumps({"module": M.__name__, "keys": {k: list(v.shape) for k, v in sd.items()},
-                  "sum": float(sum(v.double().abs().sum() for v in sd.values()))}))
-''' % ROOT
-    import json
+out = {"module": M.__name__}
+for net_module, net_class in %r:
+    Net = getattr(importlib.import_module("mmnas.model." + net_module), net_class)
+    torch.manual_seed(888)
+    net = Net(c, {"token_size": 20, "ans_size": 7, "pretrained_emb": np.zeros((20, 16), np.float32)})
+    sd = net.state_dict()
+    out[net_module] = {"keys": {k: list(v.shape) for k, v in sd.items()},
+                       "sum": float(sum(v.double().abs().sum() for v in sd.values()))}
+print(json.dumps(out))
+''' % (ROOT, REFERENCE_CALLERS)
     outs = {}
     for mode in ('ours', 'ref'):
         r = subprocess.run([sys.executable, '-c', code, mode], capture_output=True, text=True, cwd=ROOT)
         assert r.returncode == 0, r.stderr[-2000:]
         outs[mode] = json.loads(r.stdout.strip().splitlines()[-1])
+    return outs
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/mmnas'), reason='reference not mounted')
+@pytest.mark.parametrize('net_module', [m for m, _ in REFERENCE_CALLERS])
+def test_drop_in_under_the_reference_nets(reference_callers_built, net_module):
+    """install_as_mmnas(): each of the reference's own six callers (full_* train nets, hygr_* supernets) builds on the
+    CUDA-backed operators, and its state-dict keys / shapes / same-seed initial values equal those of the untouched
+    reference (checkpoint compatibility, train_vqa.py:249).  Construction only — the forward needs a GPU
+    (tests/test_gpu_reference_dropin.py)."""
+    outs = reference_callers_built
     assert outs['ours']['module'] == 'mmnas_b200.model.modules' and outs['ref']['module'] == 'mmnas.model.modules'
-    assert outs['ours']['keys'] == outs['ref']['keys']
-    assert abs(outs['ours']['sum'] - outs['ref']['sum']) < 1e-6 * outs['ref']['sum']   # same seed -> same init
+    ours, ref = outs['ours'][net_module], outs['ref'][net_module]
+    assert ours['keys'] == ref['keys']
+    assert abs(ours['sum'] - ref['sum']) < 1e-6 * ref['sum']   # same seed -> same init
