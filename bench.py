@@ -93,7 +93,7 @@ def cpu_step_fn(batch, threads=None):
             loss.backward()
             torch.nn.utils.clip_grad_norm_(net.parameters(), cfg.NET_GRAD_CLIP)
             optim.step()
-            return float(loss)
+            return float(loss.detach())
         return step, 'reference'
     from oracle import mmnas_oracle as O
     from mmnas_b200.model.nets import Net_Full
